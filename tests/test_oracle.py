@@ -1,0 +1,124 @@
+"""CPU tests: pin the plain-C restatement (oracle/vit_oracle.c) against
+ (a) the committed golden vectors in tests/golden/ (generated from the unmodified reference by
+     tests/golden/make_golden.py), and
+ (b) the compiled reference itself (oracle/_ref/libvitref.so), bit for bit, when it is present.
+The reference holds no golden vectors of its own for this path (its only end-to-end
+example needs real timm weights), so outputs of the reference run here ARE the pin."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import gf, model_path
+from oracle import ref, restatement as rs
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+
+
+def _sha(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for c in iter(lambda: f.read(1 << 24), b""):
+            h.update(c)
+    return h.hexdigest()
+
+
+def _oracle(cfg, ft):
+    path = model_path(cfg, ft)
+    vf = gf.read(path)
+    return path, vf, rs.OracleModel(vf, gf.tensor_specs)
+
+
+@pytest.mark.parametrize("cfg,ft", [("micro", "f16"), ("micro14", "f16"), ("micro", "f32"), ("tiny", "f16")])
+def test_restatement_matches_golden_bit_exact(cfg, ft):
+    g = np.load(os.path.join(GOLD, f"{cfg}_{ft}.npz"))
+    path, vf, om = _oracle(cfg, ft)
+    assert _sha(path) == str(g["model_sha256"]), "synthetic model writer drifted from the golden fixture"
+    rs.set_threads(8)
+    imgs = gf.synthetic_images(int(g["n_images"]), vf.img_size, seed=int(g["image_seed"]))
+    probs, logits = om.forward_batch(imgs)
+    # same libm + same summation order => identical bits on the box that made the fixture;
+    # elsewhere (different libm tanhf/expf) allow table-level noise.
+    np.testing.assert_allclose(logits, g["logits"], rtol=0, atol=2e-3 * np.abs(g["logits"]).max())
+    assert (np.argsort(-logits, 1)[:, :5] == np.argsort(-g["logits"], 1)[:, :5]).all()
+    np.testing.assert_allclose(probs, g["probs"], rtol=0, atol=1e-3)
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg,ft", [("micro", "q8_0"), ("tiny", "q8_0")])
+def test_restatement_matches_golden_q8_0(cfg, ft):
+    g = np.load(os.path.join(GOLD, f"{cfg}_{ft}.npz"))
+    path, vf, om = _oracle(cfg, ft)  # needs the reference quantize binary
+    assert _sha(path) == str(g["model_sha256"])
+    imgs = gf.synthetic_images(int(g["n_images"]), vf.img_size, seed=int(g["image_seed"]))
+    probs, logits = om.forward_batch(imgs)
+    np.testing.assert_allclose(logits, g["logits"], rtol=0, atol=2e-3 * np.abs(g["logits"]).max())
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg,ft", [("micro", "f16"), ("micro14", "f16"), ("micro", "f32"), ("micro", "q8_0"),
+                                    ("tiny", "f16")])
+def test_restatement_bit_exact_vs_compiled_reference(cfg, ft):
+    path, vf, om = _oracle(cfg, ft)
+    m = ref.RefModel(path)
+    imgs = gf.synthetic_images(2, vf.img_size, seed=77)
+    for i in range(2):
+        p_ref, l_ref = m.predict(imgs[i], n_threads=4)
+        p, l = om.forward(imgs[i])
+        assert np.array_equal(l, l_ref), np.abs(l - l_ref).max()
+        assert np.array_equal(p, p_ref)
+    m.close()
+
+
+@needs_ref
+def test_reference_is_thread_count_invariant():
+    path = model_path("micro", "f16")
+    m = ref.RefModel(path)
+    img = gf.synthetic_images(1, m.img, seed=3)[0]
+    outs = [m.predict(img, n_threads=t)[1] for t in (1, 3, 8)]
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    m.close()
+
+
+@needs_ref
+def test_primitives_bit_exact_vs_reference_ops():
+    L = ref.lib()
+    L.vitref_unary.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float]
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((64, 197)) * 4).astype(np.float32)
+    y = np.empty_like(x)
+    # GELU through the f16 table, every finite f16 input (ggml.c:1434-1441, 2197)
+    allh = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
+    allh = allh[np.isfinite(allh)]
+    ya = np.empty_like(allh)
+    L.vitref_unary(0, allh.ctypes.data, ya.ctypes.data, allh.size, 1, 0.0)
+    assert np.array_equal(ya, rs.gelu_table(allh))
+    # softmax rows (ggml.c:10498-10567)
+    L.vitref_unary(1, x.ctypes.data, y.ctypes.data, 197, 64, 0.0)
+    assert np.array_equal(y, rs.softmax_rows(x))
+    # f16 rounding (ggml.c:315-332)
+    assert np.array_equal(ref.round_f16(x), rs.round_f16(x))
+    # norm (ggml.c:8959-9008) == restatement layernorm with w=1,b=0
+    L.vitref_unary(2, x.ctypes.data, y.ctypes.data, 197, 64, 1e-6)
+    ones, zeros = np.ones(197, np.float32), np.zeros(197, np.float32)
+    assert np.array_equal(y, rs.layernorm(x, ones, zeros, 1e-6))
+
+
+def test_model_file_roundtrip_and_shapes():
+    path = model_path("micro", "f16")
+    vf = gf.read(path)
+    assert (vf.hidden_size, vf.num_hidden_layers, vf.num_attention_heads) == (128, 2, 2)
+    assert len([k for k in vf.tensors]) == 4 + 12 * 2 + 4
+    assert vf.tensors["patch_embed.proj.weight"].dtype == np.float16
+    assert vf.tensors["patch_embed.proj.bias"].shape == (1, 128, 1, 1)  # convert-pth-to-ggml.py:150-151
+    assert vf.tensors["pos_embed"].shape == (1, vf.n_tokens, 128)
+    assert vf.id2label[5] == "LABEL_5"
+
+
+def test_synthetic_images_are_preprocess_range():
+    x = gf.synthetic_images(2, 32, seed=1)
+    assert x.dtype == np.float32 and x.shape == (2, 32, 32, 3)
+    assert x.min() >= -2.2 and x.max() <= 2.7

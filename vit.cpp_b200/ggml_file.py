@@ -1,0 +1,217 @@
+"""Legacy-ggml ViT model files (the reference's ".gguf" files are NOT GGUF).
+
+Writer + reader for the container that reference ``convert-pth-to-ggml.py:105-158`` emits and
+reference ``vit.cpp:308-712`` (``vit_model_load``) parses:
+
+    int32 magic 0x67676d6c ("ggml", ggml.h:211)
+    int32 hidden_size, num_hidden_layers, num_attention_heads, num_classes, patch_size, img_size, ftype
+    int32 n_labels ; n_labels x { int32 id, int32 len, bytes }
+    per tensor: int32 n_dims, int32 name_len, int32 ftype(0=f32,1=f16,8=q8_0) ;
+                n_dims x int32 ne (reversed numpy shape) ; name ; raw data
+
+There are no real timm weights in this environment (no network, no timm), so ``write_synthetic``
+generates a seeded random model with the tensor names / shapes / dtypes of a timm
+``VisionTransformer.state_dict()`` (recipe from SURVEY.md 8c: well separated top-5 logits).
+The product loader is the C++ one in csrc/model_file.cpp; this module is host-side tooling for
+tests and bench.py only.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, Tuple
+
+import numpy as np
+
+GGML_FILE_MAGIC = 0x67676D6C
+QK8_0 = 32  # ggml-quants.h:42-46 block_q8_0 { f16 d; int8 qs[32]; }
+
+CONFIGS = {
+    # name: (hidden, layers, heads, patch, img)
+    "tiny": (192, 12, 3, 16, 224),
+    "small": (384, 12, 6, 16, 224),
+    "base": (768, 12, 12, 16, 224),
+    "large384": (1024, 24, 16, 16, 384),
+    # small shapes for fast unit tests (not reference configs)
+    "micro": (128, 2, 2, 16, 64),
+    "micro14": (128, 2, 2, 14, 56),
+}
+
+
+@dataclass
+class VitFile:
+    hidden_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_classes: int
+    patch_size: int
+    img_size: int
+    ftype: int
+    id2label: Dict[int, str] = field(default_factory=dict)
+    tensors: Dict[str, np.ndarray] = field(default_factory=dict)  # numpy-shaped (timm order)
+    tensor_ftype: Dict[str, int] = field(default_factory=dict)
+
+    @property
+    def n_tokens(self) -> int:
+        g = self.img_size // self.patch_size
+        return g * g + 1
+
+
+def tensor_specs(hidden: int, layers: int, classes: int, patch: int, img: int):
+    """(name, numpy shape, is_matrix) in timm state_dict order (convert-pth-to-ggml.py:126-139)."""
+    n_tok = (img // patch) ** 2 + 1
+    specs = [
+        ("cls_token", (1, 1, hidden), False),
+        ("pos_embed", (1, n_tok, hidden), False),
+        ("patch_embed.proj.weight", (hidden, 3, patch, patch), True),
+        ("patch_embed.proj.bias", (hidden,), False),
+    ]
+    for i in range(layers):
+        p = f"blocks.{i}."
+        specs += [
+            (p + "norm1.weight", (hidden,), False),
+            (p + "norm1.bias", (hidden,), False),
+            (p + "attn.qkv.weight", (3 * hidden, hidden), True),
+            (p + "attn.qkv.bias", (3 * hidden,), False),
+            (p + "attn.proj.weight", (hidden, hidden), True),
+            (p + "attn.proj.bias", (hidden,), False),
+            (p + "norm2.weight", (hidden,), False),
+            (p + "norm2.bias", (hidden,), False),
+            (p + "mlp.fc1.weight", (4 * hidden, hidden), True),
+            (p + "mlp.fc1.bias", (4 * hidden,), False),
+            (p + "mlp.fc2.weight", (hidden, 4 * hidden), True),
+            (p + "mlp.fc2.bias", (hidden,), False),
+        ]
+    specs += [
+        ("norm.weight", (hidden,), False),
+        ("norm.bias", (hidden,), False),
+        ("head.weight", (classes, hidden), True),
+        ("head.bias", (classes,), False),
+    ]
+    return specs
+
+
+def synth_tensors(hidden, layers, classes, patch, img, seed=0, round_bf16=False):
+    """Seeded synthetic weights (SURVEY.md 8c recipe)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape, is_mat in tensor_specs(hidden, layers, classes, patch, img):
+        if name == "head.weight":
+            w = rng.normal(0.0, 0.2, shape)
+        elif name.endswith("norm1.weight") or name.endswith("norm2.weight") or name == "norm.weight":
+            w = 1.0 + rng.normal(0.0, 0.02, shape)
+        elif is_mat and name.startswith("blocks."):
+            w = rng.normal(0.0, 0.05, shape)
+        else:
+            w = rng.normal(0.0, 0.02, shape)
+        w = w.astype(np.float32)
+        if round_bf16 and is_mat and name != "patch_embed.proj.weight":
+            u = w.view(np.uint32).astype(np.uint64)
+            u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16  # RNE to bf16
+            w = u.astype(np.uint32).view(np.float32)
+        out[name] = w
+    return out
+
+
+def _write_header(f, hp: Tuple[int, ...], ftype: int, classes: int):
+    hidden, layers, heads, patch, img = hp
+    f.write(struct.pack("i", GGML_FILE_MAGIC))
+    for v in (hidden, layers, heads, classes, patch, img):
+        f.write(struct.pack("i", v))
+    f.write(struct.pack("i", ftype))
+    f.write(struct.pack("i", classes))
+    for i in range(classes):
+        s = f"LABEL_{i}".encode()
+        f.write(struct.pack("i", i))
+        f.write(struct.pack("i", len(s)))
+        f.write(s)
+
+
+def write_synthetic(path: str, config: str = "tiny", ftype: int = 1, classes: int = 1000, seed: int = 0,
+                    round_bf16: bool = False) -> None:
+    """Write a synthetic model.  ftype 1: 2-D(+4-D) weights f16, rest f32 (convert-pth-to-ggml.py:143-147).
+    ftype 0: everything f32 EXCEPT the patch kernel, which the loader hard-codes as F16 (vit.cpp:515)."""
+    hidden, layers, heads, patch, img = CONFIGS[config]
+    assert ftype in (0, 1)
+    tens = synth_tensors(hidden, layers, classes, patch, img, seed, round_bf16)
+    with open(path, "wb") as f:
+        _write_header(f, (hidden, layers, heads, patch, img), ftype, classes)
+        for name, shape, is_mat in tensor_specs(hidden, layers, classes, patch, img):
+            data = tens[name]
+            ft = 1 if (is_mat and (ftype == 1 or name == "patch_embed.proj.weight")) else 0
+            data = data.astype(np.float16) if ft == 1 else data.astype(np.float32)
+            if name == "patch_embed.proj.bias":
+                data = data.reshape(1, data.shape[0], 1, 1)  # convert-pth-to-ggml.py:150-151
+            nm = name.encode()
+            f.write(struct.pack("iii", data.ndim, len(nm), ft))
+            for d in reversed(data.shape):
+                f.write(struct.pack("i", d))
+            f.write(nm)
+            data.tofile(f)
+
+
+def dequant_q8_0(raw: np.ndarray, n_elem: int) -> np.ndarray:
+    """block_q8_0 stream -> f32 (ggml-quants.c dequantize_row_q8_0): x = d * q."""
+    nb = n_elem // QK8_0
+    blk = raw.reshape(nb, 34)
+    d = blk[:, :2].copy().view(np.float16).astype(np.float32)  # [nb,1]
+    q = blk[:, 2:].copy().view(np.int8).astype(np.float32)
+    return (d * q).reshape(-1)
+
+
+def read(path: str) -> VitFile:
+    """Parse a legacy-ggml ViT file (f32 / f16 / q8_0 tensors)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    off = 0
+
+    def i32():
+        nonlocal off
+        v = struct.unpack_from("i", buf, off)[0]
+        off += 4
+        return v
+
+    magic = i32()
+    if magic != GGML_FILE_MAGIC:
+        raise ValueError("bad magic")
+    hidden, layers, heads, classes, patch, img, ftype = (i32() for _ in range(7))
+    vf = VitFile(hidden, layers, heads, classes, patch, img, ftype % 1000)
+    for _ in range(i32()):
+        k = i32()
+        ln = i32()
+        vf.id2label[k] = buf[off:off + ln].decode()
+        off += ln
+    while off < len(buf):
+        n_dims, ln, ft = i32(), i32(), i32()
+        ne = [i32() for _ in range(n_dims)]
+        name = buf[off:off + ln].decode()
+        off += ln
+        shape = tuple(reversed(ne))
+        n = int(np.prod(shape))
+        if ft == 0:
+            arr = np.frombuffer(buf, np.float32, n, off).reshape(shape)
+            off += 4 * n
+        elif ft == 1:
+            arr = np.frombuffer(buf, np.float16, n, off).reshape(shape)
+            off += 2 * n
+        elif ft == 8:
+            nbytes = n // QK8_0 * 34
+            arr = np.frombuffer(buf, np.uint8, nbytes, off).copy()
+            off += nbytes
+            vf.tensors[name + ".q8_0_raw"] = arr
+            arr = dequant_q8_0(arr, n).reshape(shape)
+        else:
+            raise ValueError(f"unsupported tensor ftype {ft}")
+        vf.tensors[name] = arr
+        vf.tensor_ftype[name] = ft
+    return vf
+
+
+def synthetic_images(batch: int, img_size: int, seed: int = 1234) -> np.ndarray:
+    """float32[B,S,S,3] HWC, values = what vit_image_preprocess can emit (vit.cpp:233-234,279-280):
+    (u8 - mean_c)/std_c with u8 ~ U{0..255}.  SURVEY.md 8d."""
+    rng = np.random.default_rng(seed)
+    u8 = rng.integers(0, 256, size=(batch, img_size, img_size, 3), dtype=np.uint8)
+    mean = np.array([123.675, 116.280, 103.530], np.float32)
+    std = np.array([58.395, 57.120, 57.375], np.float32)
+    return ((u8.astype(np.float32) - mean) / std).astype(np.float32)
