@@ -1,0 +1,129 @@
+/* vitb200.h -- C ABI of the Blackwell-native ViT forward path (drop-in boundary for staghado/vit.cpp).
+ *
+ * The reference exposes the forward path as C++ free functions in vit.h:
+ *     bool vit_model_load(const std::string&, vit_model&)                       (reference vit.h:120, vit.cpp:308-712)
+ *     int  vit_predict(const vit_model&, vit_state&, const image_f32,
+ *                      const vit_params&, std::vector<std::pair<float,int>>&)   (reference vit.h:122, vit.cpp:1004-1075)
+ * There is no plugin registry; the seam is the vit_predict function boundary.  The entry points
+ * below are what a binding at that seam needs: plain pointers and sizes, no C++ or torch types.  INTEGRATION.md
+ * shows the vit.h-side shim (vit_predict re-implemented on top of this header) and the ctypes binding.
+ *
+ * Conventions (same as the reference, SURVEY.md 8b "Error convention"): functions return 0 on success and a
+ * non-zero code on failure; a message is retrievable with vitb200_last_error(); nothing throws or aborts.
+ * An engine is bound to ONE CUDA device and is thread-compatible (not thread-safe), like vit_state.
+ */
+#ifndef VITB200_H
+#define VITB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vitb200_engine vitb200_engine;
+
+/* Mirrors the POD part of vit_hparams (reference vit.h:20-37). */
+typedef struct vitb200_hparams
+{
+    int32_t hidden_size;
+    int32_t num_hidden_layers;
+    int32_t num_attention_heads;
+    int32_t num_classes;
+    int32_t patch_size;
+    int32_t img_size;
+    int32_t ftype; /* 0 f32, 1 f16, 8 q8_0 (reference vit.cpp:385-414); 1 is implemented, others are rejected */
+    float eps;     /* layer-norm epsilon, 1e-6 in the reference (vit.h:29) */
+} vitb200_hparams;
+
+/* One host tensor, as found in vit_model::tensors (reference vit.h:88, names at vit.cpp:518-579).
+ * `type` uses ggml's type ids for the formats the loader accepts: 0 = F32, 1 = F16, 8 = Q8_0.
+ * `ne` is ggml order (ne[0] fastest). */
+typedef struct vitb200_tensor
+{
+    const char *name;
+    const void *data;
+    int32_t type;
+    int32_t n_dims;
+    int64_t ne[4];
+} vitb200_tensor;
+
+/* Create an engine from weights that already live in host memory (this is what a vit.h-side shim calls with
+ * the contents of vit_model::tensors).  Weights are repacked and uploaded once; the host arena is not retained.
+ * max_batch bounds the batch accepted by vitb200_forward*.  Replaces, per model, what the reference re-does per
+ * image in vit_predict (graph build x2, ggml_allocr, thread pool; vit.cpp:1009-1036). */
+int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *tensors, int n_tensors, int device, int max_batch,
+                   vitb200_engine **out);
+
+/* Same, reading the legacy-ggml model file the reference's vit_model_load parses (vit.cpp:308-712). */
+int vitb200_create_from_file(const char *path, int device, int max_batch, vitb200_engine **out);
+
+void vitb200_destroy(vitb200_engine *e);
+
+int vitb200_get_hparams(const vitb200_engine *e, vitb200_hparams *out);
+
+/* id2label entry of the model file (vit.cpp:356-371); NULL if absent or created from tensors. */
+const char *vitb200_label(const vitb200_engine *e, int class_id);
+
+/* Batched vit_predict with HOST buffers (host->device copy of the images and device->host copy of the results
+ * are part of the call).  images: float32[batch][img][img][3], the image_f32 layout (vit.h:98-103).
+ * Any output pointer may be NULL.  probs/logits: float32[batch][num_classes]; probs are the reference's
+ * soft-maxed `state.prediction` (vit.cpp:931-933), logits the pre-softmax node (vit.cpp:928).
+ * topk_idx/topk_prob: [batch][k], probabilities descending (the head of the reference's sorted
+ * `predictions`, vit.cpp:1047-1057). */
+int vitb200_forward(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
+                    float *topk_prob, int k);
+
+/* Same with DEVICE buffers on the engine's device, enqueued on `stream` (a cudaStream_t; NULL = the engine's own
+ * stream) without synchronising: the caller owns ordering.  This is the resident-data path bench.py times. */
+int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, float *d_probs, float *d_logits,
+                           int32_t *d_topk_idx, float *d_topk_prob, int k, void *stream);
+
+/* Number of kernels this library launched during the most recent forward call. */
+int vitb200_last_launch_count(const vitb200_engine *e);
+
+/* Per-kernel device timing for roofline reporting: while enabled, CUDA-event pairs are recorded around every
+ * launch of the tracked kernels on the stream the forward runs on.  kind: 0 patch GEMM, 1 qkv GEMM, 2 proj GEMM,
+ * 3 fc1 GEMM, 4 fc2 GEMM, 5 head GEMM, 6 attention, 7 layernorm.  profile_read synchronises the device and returns
+ * the summed duration, the launch count and the algorithmic FLOPs of one launch (0 for HBM-bound kernels). */
+int vitb200_profile_enable(vitb200_engine *e, int on);
+int vitb200_profile_read(vitb200_engine *e, int kind, double *ms_total, int *launches, double *flops_per_launch);
+
+/* Opaque handles for timing on the engine's stream (bench.py passes its own stream instead, normally). */
+void *vitb200_stream(vitb200_engine *e);
+
+const char *vitb200_last_error(void);
+
+/* ---- test / debug surface (used by tests/ only) -------------------------------------------------------- */
+
+/* Intermediates of one forward of `batch` <= max_batch images, converted to float32 on the host.
+ * Any pointer may be NULL.  Shapes per image (N = tokens, D = hidden): see oracle/vit_oracle.c vo_taps. */
+typedef struct vitb200_taps
+{
+    int32_t layer;
+    float *embed;    /* [batch][N][D]  */
+    float *ln1;      /* [batch][N][D]  */
+    float *qkv;      /* [batch][N][3D] */
+    float *attn;     /* [batch][N][D]  */
+    float *x1;       /* [batch][N][D]  */
+    float *ln2;      /* [batch][N][D]  */
+    float *h;        /* [batch][N][4D] */
+    float *x2;       /* [batch][N][D]  */
+    float *final_ln; /* [batch][D]     */
+    float *x_final;  /* [batch][N][D]  */
+} vitb200_taps;
+
+int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, float *probs, float *logits,
+                          const vitb200_taps *taps);
+
+/* Stand-alone run of the tcgen05 GEMM kernel: out[M][N] = epilogue(A[M][K] (f16 bits) x W[N][K]^T (f16 bits)).
+ * epilogue: 0 bias->f16, 1 bias+gelu->f16, 2 bias+resid->f32, 4 bias->f32.  out is float32[M][N] on the host
+ * (f16 results widened).  resid may be NULL unless epilogue == 2. */
+int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W,
+                      const float *bias, const float *resid, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITB200_H */

@@ -91,7 +91,19 @@ static inline float reduce_4x8(const float *s) {
  * them in float, in order, as separate multiply and add (gcc vectorises the multiplies of that
  * loop and keeps the adds sequential, so no fused multiply-add there -- checked in the
  * disassembly of the reference build and pinned bit-for-bit by tests/test_oracle.py). */
+/* Experiment knob (tests/bench never set it): 0 = the reference's arithmetic (default, bit-exact);
+ * 1 = same rounding points but dot products accumulated in double ("any other correct implementation");
+ * 2 = 1 + q,k,v rounded to f16 before attention; 3 = 1 + only v rounded to f16.  Used to measure the parity
+ * noise floor between non-bit-identical implementations. */
+static int g_variant = 0;
+void vo_set_variant(int v) { g_variant = v; }
+
 static float dot_ggml(int n, const float *x, const float *y, int dbl_tail) {
+    if (g_variant) {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc += (double)x[i] * (double)y[i];
+        return (float)acc;
+    }
     float s[32];
     for (int l = 0; l < 32; ++l) s[l] = 0.0f;
     const int np = n & ~31;
@@ -388,6 +400,8 @@ int vo_forward(void *mv, const float *img_hwc, float *logits_out, float *probs_o
         layernorm(x, N, D, L->norm1_w, L->norm1_b, m->eps, cur);                /* vit.cpp:808-812 */
         if (tap && taps->ln1) memcpy(taps->ln1, cur, (size_t)N * D * sizeof(float));
         linear(&L->qkv, L->qkv_b, cur, N, qkv);                                 /* vit.cpp:820-821 */
+        if (g_variant == 2) for (size_t i = 0; i < (size_t)N * 3 * D; ++i) qkv[i] = round_f16(qkv[i]);
+        if (g_variant == 3) for (int t = 0; t < N; ++t) for (int d = 2 * D; d < 3 * D; ++d) qkv[(size_t)t * 3 * D + d] = round_f16(qkv[(size_t)t * 3 * D + d]);
         if (tap && taps->qkv) memcpy(taps->qkv, qkv, (size_t)N * 3 * D * sizeof(float));
 
         { att_ctx ac = {qkv, att, N, D, hd}; par_for(H, attention_heads, &ac); }

@@ -1,0 +1,736 @@
+// engine.cu -- host side of the C ABI in include/vitb200.h: weight upload/repack, the static device arena,
+// TMA descriptors, and the fixed kernel schedule that replaces the reference's per-image graph build +
+// ggml_allocr + ggml_graph_compute thread pool (reference vit.cpp:1004-1075, ggml.c:15774-16039).
+#include "../../include/vitb200.h"
+
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace vitb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    fprintf(stderr, "vitb200: %s\n", buf); // reference convention: message on stderr + non-zero return
+    return 1;
+}
+
+#define CUDA_TRY(x)                                                                       \
+    do                                                                                    \
+    {                                                                                     \
+        cudaError_t e_ = (x);                                                             \
+        if (e_ != cudaSuccess) return fail("%s failed: %s", #x, cudaGetErrorString(e_));  \
+    } while (0)
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled tmap_encoder()
+{
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn)
+    {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D f16 row-major tensor [rows][cols] with row pitch `pitch` elements, box = 64 columns x box_rows rows,
+// SWIZZLE_128B (matches the UMMA K-major SWIZZLE_128B smem descriptor), out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows)
+{
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u", (int)r,
+                                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch, box_rows);
+    return 0;
+}
+
+struct Linear
+{
+    __half *w = nullptr; // [n_out][ld] f16, K contiguous (ggml ne0 = K)
+    float *b = nullptr;  // [n_out]
+    int n_out = 0, n_in = 0, ld = 0, bn = 256;
+    CUtensorMap tm;
+};
+
+struct Layer
+{
+    float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
+    Linear qkv, proj, fc1, fc2;
+};
+
+int pick_bn(int n_out) { return n_out >= 256 ? 256 : 128; }
+
+} // namespace
+
+struct vitb200_engine
+{
+    vitb200_hparams hp;
+    int device = 0, max_batch = 0, num_sms = 148;
+    int N = 0, NP = 0, G = 0, KP = 0, KPp = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    // weights
+    float *cls = nullptr, *pos = nullptr, *norm_w = nullptr, *norm_b = nullptr;
+    Linear patch, head;
+    std::vector<Layer> layers;
+    // activations (static arena, sized for max_batch)
+    float *d_img = nullptr, *X = nullptr, *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
+    int32_t *d_topk_idx = nullptr;
+    __half *A16 = nullptr, *QKV16 = nullptr, *H16 = nullptr, *CLS16 = nullptr, *PA = nullptr;
+    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C;
+    int max_k = 16;
+    int launches = 0;
+    std::map<int, std::string> labels;
+    // optional per-kernel timing (bench.py roofline): CUDA event pairs around tracked launches
+    bool profile = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; double flops; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(vitb200_engine *e, T **p, size_t count)
+{
+    void *q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, count * sizeof(T) + 256));
+    e->allocs.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return 0;
+}
+
+const vitb200_tensor *find_tensor(const vitb200_tensor *t, int n, const std::string &name)
+{
+    for (int i = 0; i < n; ++i)
+        if (name == t[i].name) return &t[i];
+    return nullptr;
+}
+
+int64_t nelem(const vitb200_tensor *t)
+{
+    int64_t n = 1;
+    for (int i = 0; i < t->n_dims && i < 4; ++i) n *= t->ne[i];
+    return n;
+}
+
+int upload_f32(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &name, int64_t expect, float **dst)
+{
+    const vitb200_tensor *x = find_tensor(t, n, name);
+    if (!x) return fail("missing tensor '%s'", name.c_str());
+    if (x->type != 0) return fail("tensor '%s' must be f32 (type %d)", name.c_str(), x->type);
+    if (nelem(x) != expect) return fail("tensor '%s' has wrong size: got %lld, expected %lld", name.c_str(), (long long)nelem(x), (long long)expect);
+    if (dev_alloc(e, dst, (size_t)expect)) return 1;
+    CUDA_TRY(cudaMemcpy(*dst, x->data, (size_t)expect * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// f16 matrix [n_out][n_in] -> device, row pitch padded to ld (zero filled), + its TMA descriptor
+int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &wname, const std::string &bname,
+                  int n_out, int n_in, int ld, Linear *L)
+{
+    const vitb200_tensor *w = find_tensor(t, n, wname);
+    if (!w) return fail("missing tensor '%s'", wname.c_str());
+    if (w->type != 1)
+        return fail("tensor '%s': weight type %d is not supported by this build (f16 model files only)", wname.c_str(), w->type);
+    if (nelem(w) != (int64_t)n_out * n_in) return fail("tensor '%s' has wrong size: got %lld, expected %lld", wname.c_str(), (long long)nelem(w), (long long)n_out * n_in);
+    L->n_out = n_out; L->n_in = n_in; L->ld = ld; L->bn = pick_bn(n_out);
+    if (dev_alloc(e, &L->w, (size_t)n_out * ld)) return 1;
+    CUDA_TRY(cudaMemset(L->w, 0, (size_t)n_out * ld * sizeof(__half)));
+    CUDA_TRY(cudaMemcpy2D(L->w, (size_t)ld * 2, w->data, (size_t)n_in * 2, (size_t)n_in * 2, (size_t)n_out, cudaMemcpyHostToDevice));
+    if (upload_f32(e, t, n, bname, n_out, &L->b)) return 1;
+    return make_tmap(&L->tm, L->w, (uint64_t)n_out, (uint64_t)ld, (uint64_t)ld, (uint32_t)L->bn);
+}
+
+enum ProfKind { PK_PATCH = 0, PK_QKV, PK_PROJ, PK_FC1, PK_FC2, PK_HEAD, PK_ATTN, PK_LN, PK_COUNT };
+
+struct ProfScope
+{
+    vitb200_engine *e;
+    cudaStream_t s;
+    cudaEvent_t b = nullptr;
+    ProfScope(vitb200_engine *e_, int kind, double flops, cudaStream_t s_) : e(e_), s(s_)
+    {
+        if (!e || !e->profile) { e = nullptr; return; }
+        cudaEvent_t a = nullptr;
+        auto get = [&](cudaEvent_t *ev) {
+            if (!e->event_pool.empty()) { *ev = e->event_pool.back(); e->event_pool.pop_back(); }
+            else cudaEventCreate(ev);
+        };
+        get(&a);
+        get(&b);
+        cudaEventRecord(a, s);
+        e->prof.push_back({kind, a, b, flops});
+    }
+    ~ProfScope()
+    {
+        if (e) cudaEventRecord(b, s);
+    }
+};
+
+template <int BN, int EPI>
+int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s, int num_sms)
+{
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, 0>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
+    const int tiles = m_tiles * n_tiles;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+    CUDA_TRY(cudaGetLastError());
+    if (e) e->launches++;
+    return 0;
+}
+
+int launch_gemm(vitb200_engine *e, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s, int num_sms)
+{
+#define VB_CASE(BN, EPI) if (bn == BN && epi == EPI) return launch_gemm_t<BN, EPI>(e, tmA, tmB, p, s, num_sms);
+    VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
+    VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
+    VB_CASE(256, EPI_BIAS_RESID_F32) VB_CASE(128, EPI_BIAS_RESID_F32)
+    VB_CASE(256, EPI_PATCH_F32) VB_CASE(128, EPI_PATCH_F32)
+    VB_CASE(256, EPI_BIAS_F32) VB_CASE(128, EPI_BIAS_F32)
+#undef VB_CASE
+    return fail("no GEMM instantiation for bn=%d epilogue=%d", bn, epi);
+}
+
+int launch_patchify(vitb200_engine *e, const float *img, __half *A, int B, cudaStream_t s)
+{
+    const long long total = (long long)B * e->G * e->hp.patch_size * e->G;
+    const int threads = 256;
+    const int blocks = (int)((total + threads - 1) / threads);
+    switch (e->hp.patch_size)
+    {
+    case 16: patchify_f16_kernel<16><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
+    case 14: patchify_f16_kernel<14><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
+    case 8: patchify_f16_kernel<8><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
+    case 32: patchify_f16_kernel<32><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
+    default: return fail("patch size %d not supported (8, 14, 16, 32)", e->hp.patch_size);
+    }
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+int launch_layernorm(vitb200_engine *e, const float *x, size_t x_row_stride, const float *w, const float *b, __half *y, int rows, cudaStream_t s)
+{
+    const int D = e->hp.hidden_size;
+    const int threads = 256, rows_per_block = threads / 32;
+    const int blocks = (rows + rows_per_block - 1) / rows_per_block;
+    if (D <= 4 * 128) layernorm_f16_kernel<4><<<blocks, threads, 0, s>>>(x, x_row_stride, w, b, y, rows, D, e->hp.eps);
+    else if (D <= 8 * 128) layernorm_f16_kernel<8><<<blocks, threads, 0, s>>>(x, x_row_stride, w, b, y, rows, D, e->hp.eps);
+    else if (D <= 16 * 128) layernorm_f16_kernel<16><<<blocks, threads, 0, s>>>(x, x_row_stride, w, b, y, rows, D, e->hp.eps);
+    else return fail("hidden size %d not supported (max 2048)", D);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+template <int NW>
+int launch_attention_t(vitb200_engine *e, int B, cudaStream_t s)
+{
+    const int N = e->N, D = e->hp.hidden_size, H = e->hp.num_attention_heads;
+    const int Npad = (N + ATT_KC - 1) / ATT_KC * ATT_KC;
+    const int smem = 2 * Npad * 128;
+    auto kern = attention_kernel<NW>;
+    static int smem_set = 0;
+    if (smem > smem_set)
+    {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    kern<<<B * H, NW * 32, smem, s>>>(e->QKV16, e->A16, N, D, H, Npad, 1.0f / sqrtf((float)(D / H)));
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+int launch_attention(vitb200_engine *e, int B, cudaStream_t s)
+{
+    const int qtiles = (e->N + 15) / 16;
+    if (qtiles <= 4) return launch_attention_t<4>(e, B, s);
+    if (qtiles <= 14) return launch_attention_t<7>(e, B, s);
+    return launch_attention_t<8>(e, B, s);
+}
+
+// D2H helpers for the debug taps
+int tap_f32(float *dst, const float *src, size_t n, cudaStream_t s)
+{
+    if (!dst) return 0;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int tap_f16(float *dst, const __half *src, size_t n, cudaStream_t s)
+{
+    if (!dst) return 0;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<__half> tmp(n);
+    CUDA_TRY(cudaMemcpy(tmp.data(), src, n * sizeof(__half), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) dst[i] = __half2float(tmp[i]);
+    return 0;
+}
+
+// The fixed kernel schedule == reference vit_encode_image (vit.cpp:718-941), batched over images.
+int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs, float *d_logits, int32_t *d_topk_idx,
+                float *d_topk_val, int k, cudaStream_t s, const vitb200_taps *taps)
+{
+    if (B < 1 || B > e->max_batch) return fail("batch %d out of range (1..%d)", B, e->max_batch);
+    if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
+    const int D = e->hp.hidden_size, N = e->N, T = B * N, C = e->hp.num_classes;
+    e->launches = 0;
+    __half *PA = e->PA;
+
+    // patch embedding: im2col-free gather + GEMM with conv bias + pos_embed epilogue (vit.cpp:772-797)
+    if (launch_patchify(e, d_images, PA, B, s)) return 1;
+    {
+        const int n = B * D, threads = 256;
+        cls_rows_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(e->X, e->cls, e->pos, B, N, D);
+        CUDA_TRY(cudaGetLastError());
+        e->launches++;
+    }
+    {
+        GemmParams p{};
+        p.M = B * e->NP; p.N = D; p.K = e->KPp; p.bias = e->patch.b; p.out = e->X; p.ldo = D;
+        p.pos = e->pos; p.np = e->NP; p.ntok = N;
+        ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
+        if (launch_gemm(e, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, p, s, e->num_sms)) return 1;
+    }
+    if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
+
+    for (int il = 0; il < e->hp.num_hidden_layers; ++il)
+    {
+        const Layer &L = e->layers[il];
+        const bool tap = taps && taps->layer == il;
+        {
+            ProfScope ps(e, PK_LN, 0.0, s);
+            if (launch_layernorm(e, e->X, (size_t)D, L.n1w, L.n1b, e->A16, T, s)) return 1; // vit.cpp:808-812
+        }
+        if (tap && tap_f16(taps->ln1, e->A16, (size_t)T * D, s)) return 1;
+        {
+            GemmParams p{};
+            p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.ldo = 3 * D;
+            ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
+            if (launch_gemm(e, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, p, s, e->num_sms)) return 1; // vit.cpp:820-821
+        }
+        if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s)) return 1;
+        {
+            ProfScope ps(e, PK_ATTN, 4.0 * B * e->hp.num_attention_heads * (double)N * N * 64, s);
+            if (launch_attention(e, B, s)) return 1; // vit.cpp:826-866
+        }
+        if (tap && tap_f16(taps->attn, e->A16, (size_t)T * D, s)) return 1;
+        {
+            GemmParams p{};
+            p.M = T; p.N = D; p.K = D; p.bias = L.proj.b; p.out = e->X; p.ldo = D; p.resid = e->X;
+            ProfScope ps(e, PK_PROJ, 2.0 * p.M * p.N * p.K, s);
+            if (launch_gemm(e, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, p, s, e->num_sms)) return 1; // vit.cpp:868-873
+        }
+        if (tap && tap_f32(taps->x1, e->X, (size_t)T * D, s)) return 1;
+        {
+            ProfScope ps(e, PK_LN, 0.0, s);
+            if (launch_layernorm(e, e->X, (size_t)D, L.n2w, L.n2b, e->A16, T, s)) return 1; // vit.cpp:881-885
+        }
+        if (tap && tap_f16(taps->ln2, e->A16, (size_t)T * D, s)) return 1;
+        {
+            GemmParams p{};
+            p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D;
+            ProfScope ps(e, PK_FC1, 2.0 * p.M * p.N * p.K, s);
+            if (launch_gemm(e, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, p, s, e->num_sms)) return 1; // vit.cpp:889-893
+        }
+        if (tap && tap_f16(taps->h, e->H16, (size_t)T * 4 * D, s)) return 1;
+        {
+            GemmParams p{};
+            p.M = T; p.N = D; p.K = 4 * D; p.bias = L.fc2.b; p.out = e->X; p.ldo = D; p.resid = e->X;
+            ProfScope ps(e, PK_FC2, 2.0 * p.M * p.N * p.K, s);
+            if (launch_gemm(e, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, p, s, e->num_sms)) return 1; // vit.cpp:896-900
+        }
+        if (tap && tap_f32(taps->x2, e->X, (size_t)T * D, s)) return 1;
+    }
+    if (taps && tap_f32(taps->x_final, e->X, (size_t)T * D, s)) return 1;
+
+    // pool (token 0) + final LN + head + soft-max + top-k (vit.cpp:910-933, 1047-1057)
+    if (launch_layernorm(e, e->X, (size_t)N * D, e->norm_w, e->norm_b, e->CLS16, B, s)) return 1;
+    if (taps && tap_f16(taps->final_ln, e->CLS16, (size_t)B * D, s)) return 1;
+    float *lg = d_logits ? d_logits : e->d_logits;
+    {
+        GemmParams p{};
+        p.M = B; p.N = C; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = C;
+        ProfScope ps(e, PK_HEAD, 2.0 * p.M * p.N * p.K, s);
+        if (launch_gemm(e, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, p, s, e->num_sms)) return 1;
+    }
+    if (d_probs || (k > 0 && (d_topk_idx || d_topk_val)))
+    {
+        softmax_topk_kernel<<<B, 256, (size_t)C * sizeof(float), s>>>(lg, d_probs, d_topk_idx, d_topk_val, C, k);
+        CUDA_TRY(cudaGetLastError());
+        e->launches++;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *vitb200_last_error(void) { return g_err.c_str(); }
+
+int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, int device, int max_batch, vitb200_engine **out)
+{
+    if (!hp || !t || !out) return fail("vitb200_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: the vit.cpp_b200 forward path has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    if (hp->hidden_size % hp->num_attention_heads != 0 || hp->hidden_size / hp->num_attention_heads != 64)
+        return fail("head dim %d not supported (64 only)", hp->num_attention_heads ? hp->hidden_size / hp->num_attention_heads : 0);
+    if (hp->hidden_size % 64 != 0) return fail("hidden size %d must be a multiple of 64", hp->hidden_size);
+    if (hp->img_size % hp->patch_size != 0) return fail("img_size %d not a multiple of patch_size %d", hp->img_size, hp->patch_size);
+    if (hp->num_classes % 4 != 0) return fail("num_classes %d must be a multiple of 4", hp->num_classes);
+    if (max_batch < 1) return fail("max_batch must be >= 1");
+
+    vitb200_engine *e = new vitb200_engine();
+    e->hp = *hp;
+    if (e->hp.eps <= 0.f) e->hp.eps = 1e-6f;
+    e->device = device;
+    e->max_batch = max_batch;
+    e->num_sms = prop.multiProcessorCount;
+    const int D = hp->hidden_size, P = hp->patch_size;
+    e->G = hp->img_size / P;
+    e->NP = e->G * e->G;
+    e->N = e->NP + 1;
+    e->KP = 3 * P * P;
+    e->KPp = (e->KP + 63) / 64 * 64;
+    auto bail = [&](int) { vitb200_destroy(e); return 1; };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
+
+    // ---- weights (names: reference vit.cpp:518-579)
+    if (upload_f32(e, t, n, "cls_token", D, &e->cls)) return bail(1);
+    if (upload_f32(e, t, n, "pos_embed", (int64_t)D * e->N, &e->pos)) return bail(1);
+    if (upload_linear(e, t, n, "patch_embed.proj.weight", "patch_embed.proj.bias", D, e->KP, e->KPp, &e->patch)) return bail(1);
+    e->layers.resize(hp->num_hidden_layers);
+    for (int i = 0; i < hp->num_hidden_layers; ++i)
+    {
+        Layer &L = e->layers[i];
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        if (upload_f32(e, t, n, p + "norm1.weight", D, &L.n1w) || upload_f32(e, t, n, p + "norm1.bias", D, &L.n1b) ||
+            upload_f32(e, t, n, p + "norm2.weight", D, &L.n2w) || upload_f32(e, t, n, p + "norm2.bias", D, &L.n2b))
+            return bail(1);
+        if (upload_linear(e, t, n, p + "attn.qkv.weight", p + "attn.qkv.bias", 3 * D, D, D, &L.qkv) ||
+            upload_linear(e, t, n, p + "attn.proj.weight", p + "attn.proj.bias", D, D, D, &L.proj) ||
+            upload_linear(e, t, n, p + "mlp.fc1.weight", p + "mlp.fc1.bias", 4 * D, D, D, &L.fc1) ||
+            upload_linear(e, t, n, p + "mlp.fc2.weight", p + "mlp.fc2.bias", D, 4 * D, 4 * D, &L.fc2))
+            return bail(1);
+    }
+    if (upload_f32(e, t, n, "norm.weight", D, &e->norm_w) || upload_f32(e, t, n, "norm.bias", D, &e->norm_b)) return bail(1);
+    if (upload_linear(e, t, n, "head.weight", "head.bias", hp->num_classes, D, D, &e->head)) return bail(1);
+
+    // ---- activation arena
+    const size_t B = (size_t)max_batch, T = B * e->N;
+    const size_t h16 = T * 4 * D;
+    // The patch matrix [B*NP][KPp] aliases the MLP hidden buffer (dead while the patch GEMM runs) when it fits and
+    // has no K padding; otherwise it gets its own buffer whose zeroed padding columns are never written again.
+    const size_t pa_elems = B * e->NP * e->KPp;
+    const bool pa_alias = (e->KPp == e->KP) && pa_elems <= h16;
+    if (dev_alloc(e, &e->d_img, B * 3 * hp->img_size * hp->img_size) || dev_alloc(e, &e->X, T * D) ||
+        dev_alloc(e, &e->A16, T * D) || dev_alloc(e, &e->QKV16, T * 3 * D) || dev_alloc(e, &e->H16, h16) ||
+        dev_alloc(e, &e->CLS16, B * D) || dev_alloc(e, &e->d_logits, B * hp->num_classes) ||
+        dev_alloc(e, &e->d_probs, B * hp->num_classes) || dev_alloc(e, &e->d_topk_idx, B * e->max_k) ||
+        dev_alloc(e, &e->d_topk_val, B * e->max_k))
+        return bail(1);
+    if (pa_alias) e->PA = e->H16;
+    else
+    {
+        if (dev_alloc(e, &e->PA, pa_elems)) return bail(1);
+        if (cudaMemset(e->PA, 0, pa_elems * sizeof(__half)) != cudaSuccess) return bail(fail("cudaMemset failed"));
+    }
+    if (make_tmap(&e->tmA_D, e->A16, T, D, D, GEMM_BM) || make_tmap(&e->tmA_H, e->H16, T, 4 * (uint64_t)D, 4 * (uint64_t)D, GEMM_BM) ||
+        make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, B, D, D, GEMM_BM))
+        return bail(1);
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail("device sync after upload failed"));
+    *out = e;
+    return 0;
+}
+
+void vitb200_destroy(vitb200_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (void *p : e->allocs) cudaFree(p);
+    for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int vitb200_get_hparams(const vitb200_engine *e, vitb200_hparams *out)
+{
+    if (!e || !out) return fail("null argument");
+    *out = e->hp;
+    return 0;
+}
+
+const char *vitb200_label(const vitb200_engine *e, int class_id)
+{
+    if (!e) return nullptr;
+    auto it = e->labels.find(class_id);
+    return it == e->labels.end() ? nullptr : it->second.c_str();
+}
+
+int vitb200_last_launch_count(const vitb200_engine *e) { return e ? e->launches : 0; }
+
+int vitb200_profile_enable(vitb200_engine *e, int on)
+{
+    if (!e) return fail("null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto &r : e->prof) { e->event_pool.push_back(r.a); e->event_pool.push_back(r.b); }
+    e->prof.clear();
+    e->profile = on != 0;
+    return 0;
+}
+
+int vitb200_profile_read(vitb200_engine *e, int kind, double *ms_total, int *launches, double *flops_per_launch)
+{
+    if (!e || !ms_total || !launches || !flops_per_launch) return fail("null argument");
+    if (kind < 0 || kind >= PK_COUNT) return fail("profile kind %d out of range", kind);
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    double ms = 0.0, fl = 0.0;
+    int n = 0;
+    for (auto &r : e->prof)
+    {
+        if (r.kind != kind) continue;
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; fl = r.flops; ++n;
+    }
+    *ms_total = ms; *launches = n; *flops_per_launch = fl;
+    return 0;
+}
+void *vitb200_stream(vitb200_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, float *d_probs, float *d_logits,
+                           int32_t *d_topk_idx, float *d_topk_prob, int k, void *stream)
+{
+    if (!e || !d_images) return fail("null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    return run_forward(e, d_images, batch, d_probs, d_logits, d_topk_idx, d_topk_prob, k, s, nullptr);
+}
+
+static int forward_host(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
+                        float *topk_prob, int k, const vitb200_taps *taps)
+{
+    if (!e || !images) return fail("null argument");
+    if (batch < 1 || batch > e->max_batch) return fail("batch %d out of range (1..%d)", batch, e->max_batch);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const size_t img_elems = (size_t)3 * e->hp.img_size * e->hp.img_size;
+    const int C = e->hp.num_classes;
+    CUDA_TRY(cudaMemcpyAsync(e->d_img, images, (size_t)batch * img_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    const bool want_topk = k > 0 && (topk_idx || topk_prob);
+    if (run_forward(e, e->d_img, batch, (probs || want_topk) ? e->d_probs : nullptr, e->d_logits,
+                    want_topk ? e->d_topk_idx : nullptr, want_topk ? e->d_topk_val : nullptr, want_topk ? k : 0, s, taps))
+        return 1;
+    if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx, (size_t)batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val, (size_t)batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int vitb200_forward(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
+                    float *topk_prob, int k)
+{
+    return forward_host(e, images, batch, probs, logits, topk_idx, topk_prob, k, nullptr);
+}
+
+int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, const vitb200_taps *taps)
+{
+    return forward_host(e, images, batch, probs, logits, nullptr, nullptr, 0, taps);
+}
+
+int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W, const float *bias,
+                      const float *resid, float *out)
+{
+    if (!A || !W || !bias || !out) return fail("null argument");
+    if (K % 8 != 0) return fail("K must be a multiple of 8");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    __half *dA = nullptr, *dW = nullptr;
+    float *dB = nullptr, *dR = nullptr;
+    void *dO = nullptr;
+    const bool f16out = epilogue == EPI_BIAS_F16 || epilogue == EPI_BIAS_GELU_F16;
+    const size_t osz = (size_t)M * N * (f16out ? 2 : 4);
+    int rc = 1;
+    do
+    {
+        if (cudaMalloc(&dA, (size_t)M * K * 2) || cudaMalloc(&dW, (size_t)N * K * 2) || cudaMalloc(&dB, (size_t)N * 4) || cudaMalloc(&dO, osz)) { fail("cudaMalloc failed"); break; }
+        cudaMemcpy(dA, A, (size_t)M * K * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dW, W, (size_t)N * K * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice);
+        cudaMemset(dO, 0, osz);
+        if (epilogue == EPI_BIAS_RESID_F32)
+        {
+            if (!resid) { fail("resid required"); break; }
+            if (cudaMalloc(&dR, (size_t)M * N * 4)) { fail("cudaMalloc failed"); break; }
+            cudaMemcpy(dR, resid, (size_t)M * N * 4, cudaMemcpyHostToDevice);
+        }
+        const int bn = pick_bn(N);
+        CUtensorMap tA, tB;
+        if (make_tmap(&tA, dA, M, K, K, GEMM_BM) || make_tmap(&tB, dW, N, K, K, bn)) break;
+        GemmParams p{};
+        p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.ldo = N; p.resid = dR;
+        if (launch_gemm(nullptr, bn, epilogue, tA, tB, p, 0, prop.multiProcessorCount)) break;
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { fail("GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
+        if (f16out)
+        {
+            std::vector<__half> tmp((size_t)M * N);
+            cudaMemcpy(tmp.data(), dO, osz, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < tmp.size(); ++i) out[i] = __half2float(tmp[i]);
+        }
+        else
+            cudaMemcpy(out, dO, osz, cudaMemcpyDeviceToHost);
+        rc = 0;
+    } while (0);
+    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dO); cudaFree(dR);
+    return rc;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Legacy-ggml model file reader (the format reference vit_model_load parses, vit.cpp:308-712; written by
+// convert-pth-to-ggml.py:105-158).  Validation mirrors the reference: magic, known tensor names, element
+// counts; failures return non-zero with a message, never abort.
+namespace {
+struct FileTensor
+{
+    std::string name;
+    int32_t type, n_dims;
+    int64_t ne[4];
+    size_t offset, nbytes;
+};
+} // namespace
+
+extern "C" int vitb200_create_from_file(const char *path, int device, int max_batch, vitb200_engine **out)
+{
+    if (!path || !out) return fail("null argument");
+    std::ifstream fin(path, std::ios::binary);
+    if (!fin) return fail("failed to open '%s'", path);
+    fin.seekg(0, std::ios::end);
+    const size_t fsize = (size_t)fin.tellg();
+    fin.seekg(0);
+    std::vector<char> buf(fsize);
+    fin.read(buf.data(), (std::streamsize)fsize);
+    if (!fin) return fail("failed to read '%s'", path);
+    size_t off = 0;
+    auto rd32 = [&](int32_t &v) { if (off + 4 > fsize) return false; memcpy(&v, buf.data() + off, 4); off += 4; return true; };
+    int32_t magic = 0;
+    if (!rd32(magic) || (uint32_t)magic != 0x67676d6cu) return fail("invalid model file '%s' (bad magic)", path); // GGML_FILE_MAGIC, ggml.h:211
+    vitb200_hparams hp{};
+    int32_t ftype = 0;
+    if (!rd32(hp.hidden_size) || !rd32(hp.num_hidden_layers) || !rd32(hp.num_attention_heads) || !rd32(hp.num_classes) ||
+        !rd32(hp.patch_size) || !rd32(hp.img_size) || !rd32(ftype))
+        return fail("truncated header in '%s'", path);
+    hp.ftype = ftype % 1000; // GGML_QNT_VERSION_FACTOR, vit.cpp:343-354
+    hp.eps = 1e-6f;
+    std::map<int, std::string> labels;
+    int32_t n_labels = 0;
+    if (!rd32(n_labels) || n_labels < 0) return fail("truncated label table in '%s'", path);
+    for (int i = 0; i < n_labels; ++i)
+    {
+        int32_t key = 0, len = 0;
+        if (!rd32(key) || !rd32(len) || len < 0 || off + (size_t)len > fsize) return fail("truncated label table in '%s'", path);
+        labels[key] = std::string(buf.data() + off, (size_t)len);
+        off += (size_t)len;
+    }
+    std::vector<FileTensor> fts;
+    while (off < fsize)
+    {
+        FileTensor ft{};
+        int32_t len = 0;
+        if (!rd32(ft.n_dims) || !rd32(len) || !rd32(ft.type)) return fail("truncated tensor record in '%s'", path);
+        if (ft.n_dims < 1 || ft.n_dims > 4 || len < 0) return fail("corrupt tensor record in '%s'", path);
+        int64_t ne_total = 1;
+        for (int i = 0; i < 4; ++i) ft.ne[i] = 1;
+        for (int i = 0; i < ft.n_dims; ++i)
+        {
+            int32_t d = 0;
+            if (!rd32(d) || d < 1) return fail("corrupt tensor dims in '%s'", path);
+            ft.ne[i] = d;
+            ne_total *= d;
+        }
+        if (off + (size_t)len > fsize) return fail("truncated tensor name in '%s'", path);
+        ft.name.assign(buf.data() + off, (size_t)len);
+        off += (size_t)len;
+        switch (ft.type) // vit.cpp:645-678
+        {
+        case 0: ft.nbytes = (size_t)ne_total * 4; break;
+        case 1: ft.nbytes = (size_t)ne_total * 2; break;
+        case 8: ft.nbytes = (size_t)ne_total / 32 * 34; break;
+        default: return fail("unknown ftype %d in model file (tensor '%s')", ft.type, ft.name.c_str());
+        }
+        if (off + ft.nbytes > fsize) return fail("tensor '%s' has wrong size in model file", ft.name.c_str());
+        ft.offset = off;
+        off += ft.nbytes;
+        fts.push_back(ft);
+    }
+    const int expected = 4 + 12 * hp.num_hidden_layers + 4; // vit.cpp:697
+    if ((int)fts.size() != expected) return fail("model file has %d tensors, but %d tensors were expected", (int)fts.size(), expected);
+    std::vector<vitb200_tensor> ts(fts.size());
+    for (size_t i = 0; i < fts.size(); ++i)
+    {
+        ts[i].name = fts[i].name.c_str();
+        ts[i].data = buf.data() + fts[i].offset;
+        ts[i].type = fts[i].type;
+        ts[i].n_dims = fts[i].n_dims;
+        for (int j = 0; j < 4; ++j) ts[i].ne[j] = fts[i].ne[j];
+    }
+    int rc = vitb200_create(&hp, ts.data(), (int)ts.size(), device, max_batch, out);
+    if (rc == 0) (*out)->labels = labels;
+    return rc;
+}

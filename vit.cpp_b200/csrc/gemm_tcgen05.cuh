@@ -1,0 +1,325 @@
+// gemm_tcgen05.cuh -- the linear-layer kernel: C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue.
+//
+// Replaces ggml_mul_mat + ggml_add_inplace (+ ggml_gelu) (+ residual ggml_add) of the reference graph
+// (reference vit.cpp:820-821, 868-873, 889-900, 927-928, and the conv GEMM of vit.cpp:772-797) and the CPU
+// kernel behind them (ggml.c:9388-9597 with ggml_vec_dot_f16, ggml.c:1200-1236).
+// Numerics follow the reference recipe: A = activations already rounded to f16 (RNE, ggml.c:9493-9506),
+// W = the f16 weights as stored in the model file (ne0 = K contiguous, vit.cpp:531-543), fp32 accumulation.
+//
+// Structure (sm_100a): persistent CTAs, one per SM, 6 warps:
+//   warp 0   TMA producer  : cp.async.bulk.tensor 128x64 A tile + BNx64 W tile per stage (SWIZZLE_128B)
+//   warp 1   MMA issuer    : one thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16) x4 per stage,
+//                            accumulators in TMEM (2 x BN columns, double buffered against the epilogue)
+//   warps 2-5 epilogue     : tcgen05.ld -> registers -> (bias / GELU / residual / pos-embed) -> swizzled smem
+//                            transpose -> 128-bit fully coalesced global stores
+// Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
+#pragma once
+#include "ptx.cuh"
+
+namespace vitb200 {
+
+enum GemmEpilogue
+{
+    EPI_BIAS_F16 = 0,       // out f16 = f16(acc + bias)                              (qkv)
+    EPI_BIAS_GELU_F16 = 1,  // out f16 = f16(gelu_tanh(f32(f16(acc + bias))))           (fc1; ggml.c:1418-1441)
+    EPI_BIAS_RESID_F32 = 2, // out f32 = (acc + bias) + resid                         (proj, fc2; vit.cpp:873,900)
+    EPI_PATCH_F32 = 3,      // out f32[token row] = (acc + bias) + pos_embed           (patch embed; vit.cpp:773-797)
+    EPI_BIAS_F32 = 4,       // out f32 = acc + bias                                   (head logits)
+};
+
+struct GemmParams
+{
+    int M, N, K;        // valid extents (rows of A / rows of W / reduction)
+    const float *bias;  // [N]
+    void *out;          // f16 or f32, row-major, leading dimension ldo
+    int ldo;
+    const float *resid; // EPI_BIAS_RESID_F32: [M][ldo] (may alias out)
+    const float *pos;   // EPI_PATCH_F32: pos_embed [ntok][N]
+    int np, ntok;       // EPI_PATCH_F32: patches / tokens per image
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg
+{
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = 4 * 4096; // 4 epilogue warps x 4 KB transpose buffer
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * (A_BYTES + B_BYTES) + STAGE_BYTES + BAR_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+// GELU, tanh form, exactly the reference's formula (ggml.c:1418-1424) evaluated in f32 on an f16-valued
+// input; tanh via 1 - 2/(1+e^{2u}).  The result is rounded to f16 by the caller (ggml.c:2197 table semantics).
+__device__ __forceinline__ float gelu_tanh_f32(float x)
+{
+    const float u = 0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x);
+    const float e = __expf(2.0f * u);
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + e);
+    return 0.5f * x * (1.0f + t);
+}
+
+template <int BN, int EPI, int B_FMT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
+{
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr bool kOutF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B wants 1024-B aligned tiles
+    uint8_t *smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    const uint32_t sA = smem_base;
+    const uint32_t sB = sA + kStages * Cfg::A_BYTES;
+    uint8_t *stg_base = smem + kStages * (Cfg::A_BYTES + Cfg::B_BYTES);
+    const uint32_t bars = smem_base + kStages * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STAGE_BYTES;
+    // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_ptr_addr = bars + 8u * (2 * kStages + 4);
+    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + kStages * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STAGE_BYTES + 8 * (2 * kStages + 4));
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp_idx == 0 && lane == 0)
+    {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp_idx == 1 && lane == 0)
+    {
+        for (int s = 0; s < kStages; ++s)
+        {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a)
+        {
+            ptx::mbar_init(tfull_bar(a), 1);
+            ptx::mbar_init(tempty_bar(a), 4); // one arrival per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp_idx == 2)
+    {
+        ptx::tcgen05_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+        ptx::tcgen05_relinquish();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp_idx == 0)
+    {
+        // ===================== TMA producer =====================
+        if (lane == 0)
+        {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb)
+                {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
+                    ptx::tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * GEMM_BM);
+                    ptx::tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    else if (warp_idx == 1)
+    {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0)
+        {
+            constexpr uint32_t idesc = ptx::umma_idesc_f16(GEMM_BM, BN, /*a=f16*/ 0, B_FMT);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+            {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1); // epilogue has drained this accumulator
+                ptx::tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb)
+                {
+                    ptx::mbar_wait(full_bar(stage), phase); // TMA bytes have landed
+                    ptx::tcgen05_fence_after();
+                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sA + stage * Cfg::A_BYTES);
+                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                    {
+                        // advance 16 f16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+                        ptx::tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    ptx::tcgen05_commit(empty_bar(stage)); // frees the smem slot when these MMAs retire
+                    if (kb == num_kb - 1) ptx::tcgen05_commit(tfull_bar(as)); // accumulator complete
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    else
+    {
+        // ===================== epilogue warps (2..5) =====================
+        const int q = warp_idx & 3; // TMEM lane quarter this warp may access
+        uint8_t *stg = stg_base + (warp_idx - 2) * 4096;
+        const uint32_t sw = lane & 7;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+        {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tcgen05_fence_after();
+            const int m0 = m_blk * GEMM_BM + q * 32;
+            const int n0 = n_blk * BN;
+            const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+
+            constexpr int CH = kOutF16 ? 64 : 32; // columns per pass: one 128-B row segment per thread-row
+#pragma unroll 1
+            for (int c = 0; c < BN; c += CH)
+            {
+                uint32_t v[CH];
+                {
+                    uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                    ptx::tcgen05_ld_32x32b_x32(tmem_acc + c, v0);
+                    if constexpr (CH == 64)
+                    {
+                        uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                        ptx::tcgen05_ld_32x32b_x32(tmem_acc + c + 32, v1);
+                    }
+                }
+                ptx::tcgen05_wait_ld();
+                if (c + CH == BN)
+                {
+                    // last TMEM read of this accumulator: hand it back to the MMA warp early
+                    ptx::tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+                }
+
+                if constexpr (kOutF16)
+                {
+                    // math in the row-per-thread domain (bias is warp-uniform -> broadcast loads), pack to f16
+                    uint4 *stg4 = reinterpret_cast<uint4 *>(stg);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) // 8 chunks of 8 columns (16 B of f16)
+                    {
+                        uint32_t packed[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                        {
+                            const int col = n0 + c + j * 8 + e * 2;
+                            float b0 = 0.f, b1 = 0.f;
+                            if (col < p.N) { b0 = __ldg(p.bias + col); b1 = __ldg(p.bias + col + 1); }
+                            float x0 = __uint_as_float(v[j * 8 + e * 2]) + b0;
+                            float x1 = __uint_as_float(v[j * 8 + e * 2 + 1]) + b1;
+                            __half2 h;
+                            if constexpr (EPI == EPI_BIAS_GELU_F16)
+                            {
+                                // ggml.c:1434-1441: y = f16(gelu(f32(f16(x))))
+                                const float r0 = __half2float(__float2half_rn(x0));
+                                const float r1 = __half2float(__float2half_rn(x1));
+                                h = __floats2half2_rn(gelu_tanh_f32(r0), gelu_tanh_f32(r1));
+                            }
+                            else
+                            {
+                                h = __floats2half2_rn(x0, x1);
+                            }
+                            packed[e] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        stg4[lane * 8 + (j ^ sw)] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                    {
+                        const int row = i * 4 + (lane >> 3);
+                        const int ch = lane & 7;
+                        const uint4 val = stg4[row * 8 + (ch ^ (row & 7))];
+                        const int grow = m0 + row;
+                        const int gcol = n0 + c + ch * 8;
+                        if (grow < p.M && gcol < p.N)
+                            *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out) + (size_t)grow * p.ldo + gcol) = val;
+                    }
+                    __syncwarp();
+                }
+                else
+                {
+                    // raw accumulators through the transpose buffer; bias / residual / pos math on the coalesced side
+                    float4 *stg4 = reinterpret_cast<float4 *>(stg);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        stg4[lane * 8 + (j ^ sw)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                    {
+                        const int row = i * 4 + (lane >> 3);
+                        const int ch = lane & 7;
+                        float4 a = stg4[row * 8 + (ch ^ (row & 7))];
+                        const int grow = m0 + row;
+                        const int gcol = n0 + c + ch * 4;
+                        if (grow < p.M && gcol < p.N)
+                        {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + gcol));
+                            a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+                            size_t orow = (size_t)grow;
+                            if constexpr (EPI == EPI_BIAS_RESID_F32)
+                            {
+                                const float4 r = *reinterpret_cast<const float4 *>(p.resid + (size_t)grow * p.ldo + gcol);
+                                a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
+                            }
+                            if constexpr (EPI == EPI_PATCH_F32)
+                            {
+                                const int img = grow / p.np, pp = grow - img * p.np;
+                                orow = (size_t)img * p.ntok + 1 + pp;
+                                const float4 r = __ldg(reinterpret_cast<const float4 *>(p.pos + (size_t)(1 + pp) * p.N + gcol));
+                                a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
+                            }
+                            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + orow * p.ldo + gcol) = a;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+
+    // ===================== teardown =====================
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 2)
+    {
+        ptx::tcgen05_fence_after();
+        ptx::tcgen05_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+} // namespace vitb200

@@ -1,0 +1,173 @@
+"""Host-side mirror of the reference's vit.h interface on top of the C ABI (include/vitb200.h).
+
+Names and argument meaning follow the reference (vit.h:118-122) so tests read like reference usage:
+
+    model = vit_model_load(path)                      # reference vit.cpp:308  (here: parse + upload to the GPU)
+    probs, idx, val = vit_predict(model, images)      # reference vit.cpp:1004 (here: batched, on the GPU)
+
+There is NO CPU fallback: if libvitb200.so is missing or no B200 is present these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vitb200.h")
+_lib = None
+
+
+class VitB200Error(RuntimeError):
+    pass
+
+
+class Hparams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("hidden_size", "num_hidden_layers", "num_attention_heads", "num_classes",
+                                          "patch_size", "img_size", "ftype")] + [("eps", C.c_float)]
+
+
+class Taps(C.Structure):
+    _fields_ = [("layer", C.c_int32)] + [(n, C.c_void_p) for n in
+                                         ("embed", "ln1", "qkv", "attn", "x1", "ln2", "h", "x2", "final_ln", "x_final")]
+
+
+def declared_symbols() -> list:
+    """Every function name include/vitb200.h declares (for the CPU-side ABI test)."""
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vitb200_[a-z_0-9]+)\s*\(", src)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VitB200Error(f"{LIB_PATH} is missing: build it with ./build.sh (python -c 'import __graft_entry__ as g; "
+                               "g.build()'). The vit.cpp_b200 forward path has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, f32p = C.c_void_p, C.c_int, C.c_void_p
+        L.vitb200_last_error.restype = C.c_char_p
+        L.vitb200_create_from_file.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
+        L.vitb200_create.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
+        L.vitb200_destroy.argtypes = [vp]
+        L.vitb200_destroy.restype = None
+        L.vitb200_get_hparams.argtypes = [vp, C.POINTER(Hparams)]
+        L.vitb200_label.argtypes = [vp, i32]
+        L.vitb200_label.restype = C.c_char_p
+        L.vitb200_forward.argtypes = [vp, f32p, i32, f32p, f32p, vp, f32p, i32]
+        L.vitb200_forward_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp]
+        L.vitb200_last_launch_count.argtypes = [vp]
+        L.vitb200_stream.argtypes = [vp]
+        L.vitb200_stream.restype = vp
+        L.vitb200_forward_debug.argtypes = [vp, f32p, i32, f32p, f32p, C.POINTER(Taps)]
+        L.vitb200_test_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise VitB200Error(f"{what}: {lib().vitb200_last_error().decode()}")
+
+
+class VitModel:
+    """vit_model + vit_state of the reference (vit.h:72-89), living on one GPU."""
+
+    def __init__(self, handle, device: int, max_batch: int):
+        self._h = handle
+        self.device = device
+        self.max_batch = max_batch
+        hp = Hparams()
+        _check(lib().vitb200_get_hparams(self._h, C.byref(hp)), "vitb200_get_hparams")
+        self.hparams = hp
+        self.hidden_size, self.num_classes, self.img_size = hp.hidden_size, hp.num_classes, hp.img_size
+        self.n_tokens = (hp.img_size // hp.patch_size) ** 2 + 1
+
+    def label(self, i: int) -> Optional[str]:
+        s = lib().vitb200_label(self._h, i)
+        return s.decode() if s else None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def last_launch_count(self) -> int:
+        return lib().vitb200_last_launch_count(self._h)
+
+    def close(self):
+        if self._h:
+            lib().vitb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def vit_model_load(fname: str, device: int = 0, max_batch: int = 256) -> VitModel:
+    """reference: bool vit_model_load(const std::string &fname, vit_model &model)  (vit.cpp:308)"""
+    h = C.c_void_p()
+    _check(lib().vitb200_create_from_file(fname.encode(), device, max_batch, C.byref(h)), "vit_model_load")
+    return VitModel(h, device, max_batch)
+
+
+def vit_predict(model: VitModel, images: np.ndarray, topk: int = 5, want_logits: bool = False):
+    """Batched reference vit_predict (vit.cpp:1004): images float32[B,S,S,3] (image_f32 layout) on the HOST.
+    Returns (probs[B,C], topk_idx[B,k], topk_prob[B,k]) (+ logits[B,C] if want_logits)."""
+    imgs = np.ascontiguousarray(images, dtype=np.float32)
+    if imgs.ndim == 3:
+        imgs = imgs[None]
+    B = imgs.shape[0]
+    assert imgs.shape[1:] == (model.img_size, model.img_size, 3), imgs.shape
+    probs = np.empty((B, model.num_classes), np.float32)
+    logits = np.empty((B, model.num_classes), np.float32) if want_logits else None
+    idx = np.empty((B, topk), np.int32)
+    val = np.empty((B, topk), np.float32)
+    _check(lib().vitb200_forward(model.handle, imgs.ctypes.data, B, probs.ctypes.data,
+                                 logits.ctypes.data if want_logits else None, idx.ctypes.data, val.ctypes.data, topk),
+           "vit_predict")
+    return (probs, idx, val, logits) if want_logits else (probs, idx, val)
+
+
+TAP_SHAPES = {
+    "embed": lambda B, N, D: (B, N, D), "ln1": lambda B, N, D: (B, N, D), "qkv": lambda B, N, D: (B, N, 3 * D),
+    "attn": lambda B, N, D: (B, N, D), "x1": lambda B, N, D: (B, N, D), "ln2": lambda B, N, D: (B, N, D),
+    "h": lambda B, N, D: (B, N, 4 * D), "x2": lambda B, N, D: (B, N, D), "final_ln": lambda B, N, D: (B, D),
+    "x_final": lambda B, N, D: (B, N, D),
+}
+
+
+def vit_predict_debug(model: VitModel, images: np.ndarray, tap_layer: int, taps=tuple(TAP_SHAPES)):
+    """Forward with intermediates copied back (tests only)."""
+    imgs = np.ascontiguousarray(images, dtype=np.float32)
+    B = imgs.shape[0]
+    probs = np.empty((B, model.num_classes), np.float32)
+    logits = np.empty((B, model.num_classes), np.float32)
+    tp = Taps()
+    tp.layer = tap_layer
+    out = {}
+    for n in taps:
+        out[n] = np.zeros(TAP_SHAPES[n](B, model.n_tokens, model.hidden_size), np.float32)
+        setattr(tp, n, out[n].ctypes.data)
+    _check(lib().vitb200_forward_debug(model.handle, imgs.ctypes.data, B, probs.ctypes.data, logits.ctypes.data,
+                                       C.byref(tp)), "vit_predict_debug")
+    return probs, logits, out
+
+
+def test_gemm(M: int, N: int, K: int, epilogue: int, A16: np.ndarray, W16: np.ndarray, bias: np.ndarray,
+              resid: Optional[np.ndarray] = None, device: int = 0) -> np.ndarray:
+    A = np.ascontiguousarray(A16, np.float16)
+    W = np.ascontiguousarray(W16, np.float16)
+    b = np.ascontiguousarray(bias, np.float32)
+    r = np.ascontiguousarray(resid, np.float32) if resid is not None else None
+    out = np.empty((M, N), np.float32)
+    _check(lib().vitb200_test_gemm(device, M, N, K, epilogue, A.ctypes.data, W.ctypes.data, b.ctypes.data,
+                                   r.ctypes.data if r is not None else None, out.ctypes.data), "vitb200_test_gemm")
+    return out
