@@ -75,6 +75,13 @@ const char *vitb200_label(const vitb200_engine *e, int class_id);
 int vitb200_forward(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
                     float *topk_prob, int k);
 
+/* Pipelined form of vitb200_forward: returns as soon as the work is enqueued; the host->device copy of call i+1 overlaps the
+ * kernels of call i (two input/output slots).  Host buffers (pinned memory for real overlap) must stay valid, and outputs
+ * must not be read, until vitb200_sync() returns.  vitb200_forward == vitb200_forward_async + vitb200_sync. */
+int vitb200_forward_async(vitb200_engine *e, const float *images, int batch, float *probs, float *logits,
+                          int32_t *topk_idx, float *topk_prob, int k);
+int vitb200_sync(vitb200_engine *e);
+
 /* Same with DEVICE buffers on the engine's device, enqueued on `stream` (a cudaStream_t; NULL = the engine's own
  * stream) without synchronising: the caller owns ordering.  This is the resident-data path bench.py times. */
 int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, float *d_probs, float *d_logits,

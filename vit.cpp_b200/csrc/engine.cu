@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -58,6 +59,23 @@ PFN_tmapEncodeTiled tmap_encoder()
 
 // 2-D f16 row-major tensor [rows][cols] with row pitch `pitch` elements, box = 64 columns x box_rows rows,
 // SWIZZLE_128B (matches the UMMA K-major SWIZZLE_128B smem descriptor), out-of-bounds elements read as zero.
+// 2-D f32 row-major tensor [rows][cols], box = 32 columns (128 B) x 32 rows, SWIZZLE_128B: the residual stream X as the
+// residual epilogue loads and stores it (one 4-KB box per epilogue warp and 32-column chunk).
+int make_tmap_f32_box32(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch)
+{
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(f32) failed (%d)", (int)r);
+    return 0;
+}
+
 int make_tmap(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows)
 {
     PFN_tmapEncodeTiled enc = tmap_encoder();
@@ -107,10 +125,18 @@ struct vitb200_engine
     float *d_img = nullptr, *X = nullptr, *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
     int32_t *d_topk_idx = nullptr;
     __half *A16 = nullptr, *QKV16 = nullptr, *H16 = nullptr, *CLS16 = nullptr, *PA = nullptr;
-    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C;
+    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX;
     int max_k = 16;
     int launches = 0;
     std::map<int, std::string> labels;
+    // host-buffer pipeline (vitb200_forward_async): 2 input/output slots, H2D on a copy stream overlapping the previous
+    // call's kernels on the compute stream
+    cudaStream_t copy_stream = nullptr;
+    float *d_img_slot[2] = {nullptr, nullptr}, *d_probs_slot[2] = {nullptr, nullptr}, *d_logits_slot[2] = {nullptr, nullptr};
+    float *d_topk_val_slot[2] = {nullptr, nullptr};
+    int32_t *d_topk_idx_slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    unsigned long long submits = 0;
     // optional per-kernel timing (bench.py roofline): CUDA event pairs around tracked launches
     bool profile = false;
     struct ProfRec { int kind; cudaEvent_t a, b; double flops; };
@@ -199,9 +225,9 @@ struct ProfScope
 };
 
 template <int BN, int EPI>
-int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s, int num_sms)
+int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32>;
     auto kern = gemm_tcgen05_kernel<BN, EPI, 0>;
     static bool attr_set = false;
     if (!attr_set)
@@ -212,15 +238,16 @@ int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &
     const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
     const int tiles = m_tiles * n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+    kern<<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmX, p);
     CUDA_TRY(cudaGetLastError());
     if (e) e->launches++;
     return 0;
 }
 
-int launch_gemm(vitb200_engine *e, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s, int num_sms)
+// tmX: f32 [M][ldo] map of the residual/output (EPI_BIAS_RESID_F32 only; ignored otherwise)
+int launch_gemm(vitb200_engine *e, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
-#define VB_CASE(BN, EPI) if (bn == BN && epi == EPI) return launch_gemm_t<BN, EPI>(e, tmA, tmB, p, s, num_sms);
+#define VB_CASE(BN, EPI) if (bn == BN && epi == EPI) return launch_gemm_t<BN, EPI>(e, tmA, tmB, tmX, p, s, num_sms);
     VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
     VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
     VB_CASE(256, EPI_BIAS_RESID_F32) VB_CASE(128, EPI_BIAS_RESID_F32)
@@ -330,7 +357,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         p.M = B * e->NP; p.N = D; p.K = e->KPp; p.bias = e->patch.b; p.out = e->X; p.ldo = D;
         p.pos = e->pos; p.np = e->NP; p.ntok = N;
         ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
-        if (launch_gemm(e, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
 
@@ -347,7 +374,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.ldo = 3 * D;
             ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, p, s, e->num_sms)) return 1; // vit.cpp:820-821
+            if (launch_gemm(e, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
         }
         if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s)) return 1;
         {
@@ -359,7 +386,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = D; p.K = D; p.bias = L.proj.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_PROJ, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, p, s, e->num_sms)) return 1; // vit.cpp:868-873
+            if (launch_gemm(e, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
         }
         if (tap && tap_f32(taps->x1, e->X, (size_t)T * D, s)) return 1;
         {
@@ -371,14 +398,14 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D;
             ProfScope ps(e, PK_FC1, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, p, s, e->num_sms)) return 1; // vit.cpp:889-893
+            if (launch_gemm(e, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
         }
         if (tap && tap_f16(taps->h, e->H16, (size_t)T * 4 * D, s)) return 1;
         {
             GemmParams p{};
             p.M = T; p.N = D; p.K = 4 * D; p.bias = L.fc2.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_FC2, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, p, s, e->num_sms)) return 1; // vit.cpp:896-900
+            if (launch_gemm(e, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
         }
         if (tap && tap_f32(taps->x2, e->X, (size_t)T * D, s)) return 1;
     }
@@ -392,7 +419,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         GemmParams p{};
         p.M = B; p.N = C; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = C;
         ProfScope ps(e, PK_HEAD, 2.0 * p.M * p.N * p.K, s);
-        if (launch_gemm(e, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (d_probs || (k > 0 && (d_topk_idx || d_topk_val)))
     {
@@ -477,6 +504,17 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
         dev_alloc(e, &e->d_probs, B * hp->num_classes) || dev_alloc(e, &e->d_topk_idx, B * e->max_k) ||
         dev_alloc(e, &e->d_topk_val, B * e->max_k))
         return bail(1);
+    e->d_img_slot[0] = e->d_img; e->d_probs_slot[0] = e->d_probs; e->d_logits_slot[0] = e->d_logits;
+    e->d_topk_idx_slot[0] = e->d_topk_idx; e->d_topk_val_slot[0] = e->d_topk_val;
+    if (dev_alloc(e, &e->d_img_slot[1], B * 3 * hp->img_size * hp->img_size) || dev_alloc(e, &e->d_probs_slot[1], B * hp->num_classes) ||
+        dev_alloc(e, &e->d_logits_slot[1], B * hp->num_classes) || dev_alloc(e, &e->d_topk_idx_slot[1], B * e->max_k) ||
+        dev_alloc(e, &e->d_topk_val_slot[1], B * e->max_k))
+        return bail(1);
+    if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail("cudaEventCreate failed"));
     if (pa_alias) e->PA = e->H16;
     else
     {
@@ -484,7 +522,8 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
         if (cudaMemset(e->PA, 0, pa_elems * sizeof(__half)) != cudaSuccess) return bail(fail("cudaMemset failed"));
     }
     if (make_tmap(&e->tmA_D, e->A16, T, D, D, GEMM_BM) || make_tmap(&e->tmA_H, e->H16, T, 4 * (uint64_t)D, 4 * (uint64_t)D, GEMM_BM) ||
-        make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, B, D, D, GEMM_BM))
+        make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, B, D, D, GEMM_BM) ||
+        make_tmap_f32_box32(&e->tmX, e->X, T, D, D))
         return bail(1);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail("device sync after upload failed"));
     *out = e;
@@ -499,6 +538,8 @@ void vitb200_destroy(vitb200_engine *e)
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); }
     delete e;
 }
 
@@ -558,26 +599,55 @@ int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, 
     return run_forward(e, d_images, batch, d_probs, d_logits, d_topk_idx, d_topk_prob, k, s, nullptr);
 }
 
-static int forward_host(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
-                        float *topk_prob, int k, const vitb200_taps *taps)
+// Enqueue one batched forward with HOST buffers.  Slot s = call parity: the H2D of this call runs on the copy stream and
+// may overlap the kernels of the previous call (other slot); kernels + D2H run on the compute stream in call order.
+static int forward_enqueue(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
+                           float *topk_prob, int k, const vitb200_taps *taps)
 {
     if (!e || !images) return fail("null argument");
     if (batch < 1 || batch > e->max_batch) return fail("batch %d out of range (1..%d)", batch, e->max_batch);
     CUDA_TRY(cudaSetDevice(e->device));
-    cudaStream_t s = e->stream;
+    const int sl = (int)(e->submits & 1);
+    cudaStream_t s = e->stream, cs = e->copy_stream;
     const size_t img_elems = (size_t)3 * e->hp.img_size * e->hp.img_size;
     const int C = e->hp.num_classes;
-    CUDA_TRY(cudaMemcpyAsync(e->d_img, images, (size_t)batch * img_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (e->submits >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, e->ev_done[sl], 0)); // slot's previous forward has consumed its inputs/outputs
+    CUDA_TRY(cudaMemcpyAsync(e->d_img_slot[sl], images, (size_t)batch * img_elems * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaEventRecord(e->ev_h2d[sl], cs));
+    CUDA_TRY(cudaStreamWaitEvent(s, e->ev_h2d[sl], 0));
     const bool want_topk = k > 0 && (topk_idx || topk_prob);
-    if (run_forward(e, e->d_img, batch, (probs || want_topk) ? e->d_probs : nullptr, e->d_logits,
-                    want_topk ? e->d_topk_idx : nullptr, want_topk ? e->d_topk_val : nullptr, want_topk ? k : 0, s, taps))
+    if (run_forward(e, e->d_img_slot[sl], batch, (probs || want_topk) ? e->d_probs_slot[sl] : nullptr, e->d_logits_slot[sl],
+                    want_topk ? e->d_topk_idx_slot[sl] : nullptr, want_topk ? e->d_topk_val_slot[sl] : nullptr, want_topk ? k : 0, s, taps))
         return 1;
-    if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx, (size_t)batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val, (size_t)batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs_slot[sl], (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits_slot[sl], (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx_slot[sl], (size_t)batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val_slot[sl], (size_t)batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(e->ev_done[sl], s));
+    e->submits++;
     return 0;
+}
+
+int vitb200_forward_async(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
+                          float *topk_prob, int k)
+{
+    return forward_enqueue(e, images, batch, probs, logits, topk_idx, topk_prob, k, nullptr);
+}
+
+int vitb200_sync(vitb200_engine *e)
+{
+    if (!e) return fail("null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int forward_host(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
+                        float *topk_prob, int k, const vitb200_taps *taps)
+{
+    if (forward_enqueue(e, images, batch, probs, logits, topk_idx, topk_prob, k, taps)) return 1;
+    return vitb200_sync(e);
 }
 
 int vitb200_forward(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,
@@ -619,11 +689,18 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
             cudaMemcpy(dR, resid, (size_t)M * N * 4, cudaMemcpyHostToDevice);
         }
         const int bn = pick_bn(N);
-        CUtensorMap tA, tB;
+        CUtensorMap tA, tB, tX;
         if (make_tmap(&tA, dA, M, K, K, GEMM_BM) || make_tmap(&tB, dW, N, K, K, bn)) break;
+        memset(&tX, 0, sizeof(tX));
+        if (epilogue == EPI_BIAS_RESID_F32)
+        {
+            // the residual epilogue works in place on the f32 stream, like the engine uses it (X += ...)
+            cudaMemcpy(dO, dR, (size_t)M * N * 4, cudaMemcpyDeviceToDevice);
+            if (make_tmap_f32_box32(&tX, dO, M, N, N)) break;
+        }
         GemmParams p{};
-        p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.ldo = N; p.resid = dR;
-        if (launch_gemm(nullptr, bn, epilogue, tA, tB, p, 0, prop.multiProcessorCount)) break;
+        p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.ldo = N; p.resid = (const float *)dO;
+        if (launch_gemm(nullptr, bn, epilogue, tA, tB, tX, p, 0, prop.multiProcessorCount)) break;
         cudaError_t err = cudaDeviceSynchronize();
         if (err != cudaSuccess) { fail("GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
         if (f16out)

@@ -40,18 +40,26 @@ struct GemmParams
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
 
-template <int BN>
+// The residual epilogue (proj, fc2) streams the f32 residual tile through a per-warp TMA ring (kResidRing slots of
+// 32 rows x 32 columns = 4 KB) and stores the result with TMA from the same slot, so ~64 KB of residual loads are in
+// flight per SM without holding registers; it pays for the ring with one fewer operand stage.
+template <int BN, bool kResid>
 struct GemmCfg
 {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kResidRing = 5;
+    // epilogue warps: 4 for the TMA-ring residual epilogue (HBM-bound), 8 otherwise (two per TMEM lane quarter, splitting
+    // the columns) so the ALU-heavy f16 epilogues (bias, GELU, packing) have two warps per SM sub-partition to overlap
+    static constexpr int kEpiWarps = kResid ? 4 : 8;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kStages = kResid ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 4 : 6);
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
-    static constexpr int STAGE_BYTES = 4 * 4096; // 4 epilogue warps x 4 KB transpose buffer
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int STAGE_BYTES = kResid ? 4 * kResidRing * 4096 : kEpiWarps * 4096; // per epilogue warp: ring or transpose buffer
+    static constexpr int BAR_BYTES = 512;
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * (A_BYTES + B_BYTES) + STAGE_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
 // GELU, tanh form, exactly the reference's formula (ggml.c:1418-1424) evaluated in f32 on an f16-valued
@@ -65,10 +73,12 @@ __device__ __forceinline__ float gelu_tanh_f32(float x)
 }
 
 template <int BN, int EPI, int B_FMT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32>::kThreads), 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmX, const GemmParams p)
 {
-    using Cfg = GemmCfg<BN>;
+    constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32);
+    using Cfg = GemmCfg<BN, kResid>;
     constexpr int kStages = Cfg::kStages;
     constexpr bool kOutF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
 
@@ -85,6 +95,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
     const uint32_t tmem_ptr_addr = bars + 8u * (2 * kStages + 4);
+    // residual ring "full" barriers: [4 epilogue warps][kResidRing], after the tmem pointer slot
+    auto rfull_bar = [&](int w, int r) { return bars + 8u * (2 * kStages + 6 + w * Cfg::kResidRing + r); };
     volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + kStages * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STAGE_BYTES + 8 * (2 * kStages + 4));
 
     const int warp_idx = threadIdx.x >> 5;
@@ -99,6 +111,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
+        if constexpr (kResid) ptx::prefetch_tensormap(&tmX);
     }
     if (warp_idx == 1 && lane == 0)
     {
@@ -110,8 +123,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int a = 0; a < 2; ++a)
         {
             ptx::mbar_init(tfull_bar(a), 1);
-            ptx::mbar_init(tempty_bar(a), 4); // one arrival per epilogue warp
+            ptx::mbar_init(tempty_bar(a), Cfg::kEpiWarps); // one arrival per epilogue warp
         }
+        if constexpr (kResid)
+            for (int w = 0; w < 4; ++w)
+                for (int r = 0; r < Cfg::kResidRing; ++r) ptx::mbar_init(rfull_bar(w, r), 1);
         ptx::fence_barrier_init();
     }
     if (warp_idx == 2)
@@ -186,9 +202,94 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
         // ===================== epilogue warps (2..5) =====================
         const int q = warp_idx & 3; // TMEM lane quarter this warp may access
-        uint8_t *stg = stg_base + (warp_idx - 2) * 4096;
         const uint32_t sw = lane & 7;
         int it = 0;
+        if constexpr (kResid)
+        {
+            // out = (acc + bias) + resid, f32.  Per warp: a ring of 4-KB slots, each one 32 rows x 32 f32 columns in the
+            // TMA SWIZZLE_128B layout (16-B chunk c of row r at chunk position c ^ (r & 7)).  Lane 0 keeps kResidRing-1
+            // residual loads in flight (across tile boundaries); every lane then adds its accumulator row segment in
+            // place and lane 0 TMA-stores the slot.  In-place on X is safe: a chunk is stored only after its own load
+            // completed, and prefetched chunks belong to other tiles / columns.
+            constexpr int R = Cfg::kResidRing;
+            const int ew = warp_idx - 2;
+            uint8_t *ring = stg_base + ew * (R * 4096);
+            const uint32_t ring_u32 = ptx::smem_u32(ring);
+            auto n_chunks_of = [&](int tile) { const int n0 = (tile % n_tiles) * BN; const int rem = p.N - n0; return (rem >= BN ? BN : rem + 31) / 32; };
+            // prefetch cursor
+            int pf_tile = blockIdx.x, pf_chunk = 0, pf_count = 0;
+            auto issue_next = [&]() {
+                if (pf_tile >= num_tiles) return;
+                const int slot = pf_count % R;
+                const int row0 = (pf_tile / n_tiles) * GEMM_BM + q * 32;
+                const int col0 = (pf_tile % n_tiles) * BN + pf_chunk * 32;
+                ptx::mbar_arrive_expect_tx(rfull_bar(ew, slot), 4096);
+                ptx::tma_load_2d(ring_u32 + slot * 4096, &tmX, rfull_bar(ew, slot), col0, row0);
+                ++pf_count;
+                if (++pf_chunk == n_chunks_of(pf_tile)) { pf_chunk = 0; pf_tile += gridDim.x; }
+            };
+            if (lane == 0)
+                for (int i = 0; i < R - 1; ++i) issue_next();
+            int cons = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+            {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(tfull_bar(as), aphase);
+                ptx::tcgen05_fence_after();
+                const int m0 = m_blk * GEMM_BM + q * 32;
+                const int n0 = n_blk * BN;
+                const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+                const int nch = n_chunks_of(tile);
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c, ++cons)
+                {
+                    uint32_t v[32];
+                    ptx::tcgen05_ld_32x32b_x32(tmem_acc + c * 32, v);
+                    ptx::tcgen05_wait_ld();
+                    if (c == nch - 1)
+                    {
+                        ptx::tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+                    }
+                    const int slot = cons % R;
+                    ptx::mbar_wait(rfull_bar(ew, slot), (cons / R) & 1);
+                    float4 *sl = reinterpret_cast<float4 *>(ring + slot * 4096);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                    {
+                        const int col = n0 + c * 32 + j * 4;
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col < p.N) b = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                        float4 r = sl[lane * 8 + (j ^ sw)];
+                        r.x = __fadd_rn(__fadd_rn(__uint_as_float(v[4 * j + 0]), b.x), r.x); // (mul_mat + b) + inpL, vit.cpp:869,873
+                        r.y = __fadd_rn(__fadd_rn(__uint_as_float(v[4 * j + 1]), b.y), r.y);
+                        r.z = __fadd_rn(__fadd_rn(__uint_as_float(v[4 * j + 2]), b.z), r.z);
+                        r.w = __fadd_rn(__fadd_rn(__uint_as_float(v[4 * j + 3]), b.w), r.w);
+                        sl[lane * 8 + (j ^ sw)] = r;
+                    }
+                    ptx::fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the TMA store
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        ptx::tma_store_2d(&tmX, ring_u32 + slot * 4096, n0 + c * 32, m0);
+                        ptx::tma_store_commit();
+                        // the slot of the PREVIOUS chunk is the next prefetch target: its store must have drained smem
+                        ptx::tma_store_wait_read<1>();
+                        issue_next();
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+        }
+        else
+        {
+        uint8_t *stg = stg_base + (warp_idx - 2) * 4096;
+        const int half_sel = (warp_idx - 2) >> 2; // warps w and w+4 share a TMEM lane quarter and alternate column passes
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
         {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -201,9 +302,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 
             constexpr int CH = kOutF16 ? 64 : 32; // columns per pass: one 128-B row segment per thread-row
+            constexpr int kPasses = BN / CH;
+            static_assert(kPasses % 2 == 0, "column passes must split evenly between the two warps of a quarter");
 #pragma unroll 1
-            for (int c = 0; c < BN; c += CH)
+            for (int cp = half_sel; cp < kPasses; cp += 2)
             {
+                const int c = cp * CH;
                 uint32_t v[CH];
                 {
                     uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
@@ -215,9 +319,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
                 ptx::tcgen05_wait_ld();
-                if (c + CH == BN)
+                if (cp + 2 >= kPasses)
                 {
-                    // last TMEM read of this accumulator: hand it back to the MMA warp early
+                    // this warp's last TMEM read of this accumulator: hand it back to the MMA warp early
                     ptx::tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
@@ -231,14 +335,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int j = 0; j < 8; ++j) // 8 chunks of 8 columns (16 B of f16)
                     {
                         uint32_t packed[4];
+                        float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (n0 + c + j * 8 < p.N) // N % 8 == 0 for f16 outputs: a chunk of 8 columns is all-in or all-out
+                        {
+                            const float4 bl = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + j * 8));
+                            const float4 bh = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + j * 8 + 4));
+                            bias8[0] = bl.x; bias8[1] = bl.y; bias8[2] = bl.z; bias8[3] = bl.w;
+                            bias8[4] = bh.x; bias8[5] = bh.y; bias8[6] = bh.z; bias8[7] = bh.w;
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                         {
-                            const int col = n0 + c + j * 8 + e * 2;
-                            float b0 = 0.f, b1 = 0.f;
-                            if (col < p.N) { b0 = __ldg(p.bias + col); b1 = __ldg(p.bias + col + 1); }
-                            float x0 = __uint_as_float(v[j * 8 + e * 2]) + b0;
-                            float x1 = __uint_as_float(v[j * 8 + e * 2 + 1]) + b1;
+                            float x0 = __uint_as_float(v[j * 8 + e * 2]) + bias8[e * 2];
+                            float x1 = __uint_as_float(v[j * 8 + e * 2 + 1]) + bias8[e * 2 + 1];
                             __half2 h;
                             if constexpr (EPI == EPI_BIAS_GELU_F16)
                             {
@@ -310,6 +419,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         }
+        } // !kResid
     }
 
     // ===================== teardown =====================

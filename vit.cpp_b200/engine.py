@@ -60,6 +60,10 @@ def lib():
         L.vitb200_label.argtypes = [vp, i32]
         L.vitb200_label.restype = C.c_char_p
         L.vitb200_forward.argtypes = [vp, f32p, i32, f32p, f32p, vp, f32p, i32]
+        L.vitb200_forward_async.argtypes = [vp, f32p, i32, f32p, f32p, vp, f32p, i32]
+        L.vitb200_sync.argtypes = [vp]
+        L.vitb200_profile_enable.argtypes = [vp, i32]
+        L.vitb200_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.vitb200_forward_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp]
         L.vitb200_last_launch_count.argtypes = [vp]
         L.vitb200_stream.argtypes = [vp]
