@@ -1,0 +1,308 @@
+// attention_tcgen05.cuh -- fused attention for one (image, head) per CTA iteration on the 5th-gen tensor cores.
+//
+// Replaces the reference's 16 reshape/permute/CONT nodes + mul_mat(K,Q) + scale + soft_max_inplace + mul_mat(V,P) + head
+// merge (reference vit.cpp:826-866; CPU kernels ggml.c:1163-1198 (f32 dot), 10498-10567 (soft-max)).
+//
+//   S = Q K^T      tcgen05.mma SS: A = Q tile (128 x 64, K-major, TMA SWIZZLE_128B), B = K (NKP x 64, K-major), D in TMEM
+//   P = softmax    thread = query row = TMEM lane: TRUE row max (2 TMEM passes), e = f16(exp(f16(s/8 - max))) exactly the
+//                  reference's table semantics (ggml.c:10547-10549), un-normalised P written back into the S columns as packed
+//                  f16 (tcgen05.st), l = sum e in f32
+//   O = P V        tcgen05.mma TS: A = P from TMEM, B = V (NKP x 64, MN-major, same TMA tile), D in TMEM; O * (1/l) -> f16
+//
+// Q, K, V are read straight out of the [tokens][3*D] QKV buffer by TMA (column offset h*64 / D + h*64 / 2D + h*64): no
+// split / transpose copies.  Persistent CTAs (1 per SM), 10 warps: warp 0 TMA producer (2-stage ring over problems),
+// warp 1 MMA issuer, warps 2-5 / 6-9 soft-max + epilogue warpgroups for query tile 0 / 1 (rows 0-127 / 128-255).
+// Supports N <= 224 tokens (keys padded to NKP = ceil16(N) <= 224: S0 at TMEM cols [0,224), S1 at [224,448), O at [448,512)).
+#pragma once
+#include "kernels.cuh"
+
+namespace vitb200 {
+
+struct AttnTcParams
+{
+    __half *out;  // [T][D]
+    int N, D, H;  // tokens per image, hidden, heads
+    int n_problems; // B * H
+    int NKP;      // keys padded to a multiple of 16
+    int n_mtiles; // 1 or 2 query tiles of 128 rows
+    int kv_bytes; // NKP * 128 rounded up to 1024
+    float scale;  // 1/sqrt(64)
+};
+
+constexpr int ATT_TC_THREADS = 320;
+constexpr int ATT_TC_SCOL1 = 224, ATT_TC_OCOL = 448;
+
+__device__ __forceinline__ uint32_t att_exp_pair(float x0, float x1, float &lsum)
+{
+    // e = f16(exp(f32(f16(x))))  (ggml.c:10547-10549), two elements at a time
+    const float2 xr = __half22float2(__floats2half2_rn(x0, x1));
+    const __half2 e = __floats2half2_rn(__expf(xr.x), __expf(xr.y));
+    const float2 ef = __half22float2(e);
+    lsum += ef.x + ef.y;
+    return *reinterpret_cast<const uint32_t *>(&e);
+}
+
+__global__ void __launch_bounds__(ATT_TC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcParams p)
+{
+    extern __shared__ uint8_t att_tc_smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(att_tc_smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = att_tc_smem_raw + (smem_base - ptx::smem_u32(att_tc_smem_raw));
+    const uint32_t stage_bytes = 2 * 16384 + 2 * p.kv_bytes;
+    auto sQ = [&](int st, int t) { return smem_base + st * stage_bytes + t * 16384; };
+    auto sK = [&](int st) { return smem_base + st * stage_bytes + 2 * 16384; };
+    auto sV = [&](int st) { return smem_base + st * stage_bytes + 2 * 16384 + p.kv_bytes; };
+    const uint32_t bars = smem_base + 2 * stage_bytes;
+    // barriers: load_full[2], load_empty[2], s_full[2], p_ready[2], o_full[2], o_empty[2], tmem ptr
+    auto load_full = [&](int s) { return bars + 8u * s; };
+    auto load_empty = [&](int s) { return bars + 8u * (2 + s); };
+    auto s_full = [&](int t) { return bars + 8u * (4 + t); };
+    auto p_ready = [&](int t) { return bars + 8u * (6 + t); };
+    auto o_full = [&](int t) { return bars + 8u * (8 + t); };
+    auto o_empty = [&](int t) { return bars + 8u * (10 + t); };
+    const uint32_t tmem_ptr_addr = bars + 8u * 12;
+    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + 2 * stage_bytes + 8 * 12);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp_idx == 0 && lane == 0)
+    {
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmKV);
+    }
+    if (warp_idx == 1 && lane == 0)
+    {
+        for (int i = 0; i < 2; ++i)
+        {
+            ptx::mbar_init(load_full(i), 1);
+            ptx::mbar_init(load_empty(i), 1);
+            ptx::mbar_init(s_full(i), 1);
+            ptx::mbar_init(p_ready(i), 4);
+            ptx::mbar_init(o_full(i), 1);
+            ptx::mbar_init(o_empty(i), 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp_idx == 2)
+    {
+        ptx::tcgen05_alloc(tmem_ptr_addr, 512);
+        ptx::tcgen05_relinquish();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    const uint32_t scol[2] = {0u, (uint32_t)ATT_TC_SCOL1};
+
+    if (warp_idx == 0)
+    {
+        // ===================== TMA producer =====================
+        if (lane == 0)
+        {
+            int i = 0;
+            for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
+            {
+                const int st = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                const int b = prob / p.H, h = prob - b * p.H;
+                const int row0 = b * p.N;
+                ptx::mbar_wait(load_empty(st), ph ^ 1);
+                ptx::mbar_arrive_expect_tx(load_full(st), (uint32_t)(p.n_mtiles * 16384 + 2 * p.NKP * 128));
+                ptx::tma_load_2d(sK(st), &tmKV, load_full(st), p.D + h * 64, row0);
+                ptx::tma_load_2d(sQ(st, 0), &tmQ, load_full(st), h * 64, row0);
+                if (p.n_mtiles == 2) ptx::tma_load_2d(sQ(st, 1), &tmQ, load_full(st), h * 64, row0 + 128);
+                ptx::tma_load_2d(sV(st), &tmKV, load_full(st), 2 * p.D + h * 64, row0);
+            }
+        }
+        __syncwarp();
+    }
+    else if (warp_idx == 1)
+    {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0)
+        {
+            const uint32_t idesc_s = ptx::umma_idesc_f16(128, p.NKP, 0, 0, 0, 0);
+            const uint32_t idesc_o = ptx::umma_idesc_f16(128, 64, 0, 0, 0, /*B (V) is MN-major*/ 1);
+            const int ksteps = p.NKP / 16;
+            int i = 0;
+            for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
+            {
+                const int st = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                ptx::mbar_wait(load_full(st), ph);
+                ptx::tcgen05_fence_after();
+                const uint64_t kdesc = ptx::umma_desc_kmajor_sw128(sK(st));
+                for (int t = 0; t < p.n_mtiles; ++t)
+                {
+                    // S_t = Q_t K^T.  The in-order tensor pipe runs this after P_t V of the previous problem, whose
+                    // p_ready wait guarantees the soft-max warps are done with the old S_t / P_t columns.
+                    const uint64_t qdesc = ptx::umma_desc_kmajor_sw128(sQ(st, t));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::tcgen05_mma_f16(tmem_base + scol[t], qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0);
+                    ptx::tcgen05_commit(s_full(t));
+                }
+                const uint64_t vdesc = ptx::umma_desc_mnmajor_sw128(sV(st), (uint32_t)p.kv_bytes);
+                for (int t = 0; t < p.n_mtiles; ++t)
+                {
+                    ptx::mbar_wait(p_ready(t), i & 1); // P_t is in TMEM
+                    // the single O accumulator must have been drained by its previous user
+                    if (t == 0) { if (i > 0) ptx::mbar_wait(o_empty(p.n_mtiles - 1), (i - 1) & 1); }
+                    else ptx::mbar_wait(o_empty(0), i & 1);
+                    ptx::tcgen05_fence_after();
+                    for (int j = 0; j < ksteps; ++j) // 16 keys per step: 8 TMEM columns of packed f16, 16 rows (2048 B) of V
+                        ptx::tcgen05_mma_f16_ts(tmem_base + ATT_TC_OCOL, tmem_base + scol[t] + 8 * j, vdesc + (uint64_t)(j * 128), idesc_o, j > 0);
+                    ptx::tcgen05_commit(o_full(t));
+                }
+                ptx::tcgen05_commit(load_empty(st)); // all MMAs reading this smem stage have retired
+            }
+        }
+        __syncwarp();
+    }
+    else
+    {
+        // ===================== soft-max + epilogue warpgroups =====================
+        const int t = (warp_idx - 2) >> 2; // query tile
+        const int q = warp_idx & 3;        // TMEM lane quarter
+        if (t < p.n_mtiles)
+        {
+            const int qrow = t * 128 + q * 32 + lane;          // query index within the image
+            const bool warp_valid = (t * 128 + q * 32) < p.N;  // warp owns at least one real query row
+            const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + scol[t];
+            const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + ATT_TC_OCOL;
+            const int n32 = p.NKP >> 5;
+            const bool tail16 = (p.NKP & 16) != 0;
+            int i = 0;
+            for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
+            {
+                const int b = prob / p.H, h = prob - b * p.H;
+                ptx::mbar_wait(s_full(t), i & 1);
+                ptx::tcgen05_fence_after();
+                float lsum = 0.f;
+                if (warp_valid)
+                {
+                    // ---- pass 1: true row maximum over the valid keys (ggml.c:10533-10534)
+                    float mx = -INFINITY;
+                    for (int c = 0; c < n32; ++c)
+                    {
+                        uint32_t v[32];
+                        ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, v);
+                        ptx::tcgen05_wait_ld();
+                        if (c * 32 + 32 <= p.N)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        }
+                    }
+                    if (tail16)
+                    {
+                        uint32_t v[16];
+                        ptx::tcgen05_ld_32x32b_x16(t_s + n32 * 32, v);
+                        ptx::tcgen05_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n32 * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                    const float mxs = mx * p.scale; // ggml_scale_inplace (vit.cpp:851-854); exact, scale = 1/8
+                    // ---- pass 2: P = f16(exp(f16(s*scale - max))) -> packed f16 into the S columns, l = sum P
+                    for (int c = 0; c < n32; ++c)
+                    {
+                        uint32_t v[32], pk[16];
+                        ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, v);
+                        ptx::tcgen05_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                        {
+                            const int key = c * 32 + 2 * j;
+                            float l2 = 0.f;
+                            uint32_t e = att_exp_pair(__fmaf_rn(__uint_as_float(v[2 * j]), p.scale, -mxs),
+                                                      __fmaf_rn(__uint_as_float(v[2 * j + 1]), p.scale, -mxs), l2);
+                            if (key + 1 >= p.N) // masked keys contribute exactly zero
+                            {
+                                if (key >= p.N) { e = 0u; l2 = 0.f; }
+                                else { e &= 0xFFFFu; l2 = __half2float(__ushort_as_half((unsigned short)(e & 0xFFFFu))); }
+                            }
+                            pk[j] = e;
+                            lsum += l2;
+                        }
+                        ptx::tcgen05_st_32x32b_x16(t_s + c * 16, pk);
+                    }
+                    if (tail16)
+                    {
+                        uint32_t v[16], pk[8];
+                        ptx::tcgen05_ld_32x32b_x16(t_s + n32 * 32, v);
+                        ptx::tcgen05_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                        {
+                            const int key = n32 * 32 + 2 * j;
+                            float l2 = 0.f;
+                            uint32_t e = att_exp_pair(__fmaf_rn(__uint_as_float(v[2 * j]), p.scale, -mxs),
+                                                      __fmaf_rn(__uint_as_float(v[2 * j + 1]), p.scale, -mxs), l2);
+                            if (key + 1 >= p.N)
+                            {
+                                if (key >= p.N) { e = 0u; l2 = 0.f; }
+                                else { e &= 0xFFFFu; l2 = __half2float(__ushort_as_half((unsigned short)(e & 0xFFFFu))); }
+                            }
+                            pk[j] = e;
+                            lsum += l2;
+                        }
+                        ptx::tcgen05_st_32x32b_x8(t_s + n32 * 16, pk);
+                    }
+                    ptx::tcgen05_wait_st();
+                }
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(p_ready(t));
+
+                // ---- O_t = P_t V is complete: drain, release, normalise, store
+                ptx::mbar_wait(o_full(t), i & 1);
+                ptx::tcgen05_fence_after();
+                uint32_t o[64];
+                if (warp_valid)
+                {
+                    uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[0]);
+                    uint32_t(&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[32]);
+                    ptx::tcgen05_ld_32x32b_x32(t_o, o0);
+                    ptx::tcgen05_ld_32x32b_x32(t_o + 32, o1);
+                    ptx::tcgen05_wait_ld();
+                }
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(o_empty(t));
+                if (warp_valid && qrow < p.N)
+                {
+                    const float inv = 1.0f / lsum; // p_i = e_i * (1/sum)  (ggml.c:10556-10558)
+                    uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((size_t)b * p.N + qrow) * p.D + h * 64);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                    {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                        {
+                            const __half2 hv = __floats2half2_rn(__uint_as_float(o[j * 8 + 2 * e]) * inv, __uint_as_float(o[j * 8 + 2 * e + 1]) * inv);
+                            w[e] = *reinterpret_cast<const uint32_t *>(&hv);
+                        }
+                        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 2)
+    {
+        ptx::tcgen05_fence_after();
+        ptx::tcgen05_dealloc(tmem_base, 512);
+    }
+}
+
+} // namespace vitb200

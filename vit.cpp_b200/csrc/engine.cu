@@ -5,6 +5,7 @@
 
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
+#include "attention_tcgen05.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -125,7 +126,8 @@ struct vitb200_engine
     float *d_img = nullptr, *X = nullptr, *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
     int32_t *d_topk_idx = nullptr;
     __half *A16 = nullptr, *QKV16 = nullptr, *H16 = nullptr, *CLS16 = nullptr, *PA = nullptr;
-    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX;
+    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX, tmQ, tmKV;
+    bool attn_tc = false; // tcgen05 attention (N <= 224); longer sequences use the mma.sync two-pass kernel
     int max_k = 16;
     int launches = 0;
     std::map<int, std::string> labels;
@@ -308,8 +310,32 @@ int launch_attention_t(vitb200_engine *e, int B, cudaStream_t s)
     return 0;
 }
 
+int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
+{
+    AttnTcParams p{};
+    p.out = e->A16; p.N = e->N; p.D = e->hp.hidden_size; p.H = e->hp.num_attention_heads;
+    p.n_problems = B * p.H;
+    p.NKP = (e->N + 15) / 16 * 16;
+    p.n_mtiles = (e->N + 127) / 128;
+    p.kv_bytes = (p.NKP * 128 + 1023) / 1024 * 1024;
+    p.scale = 1.0f / sqrtf((float)(p.D / p.H));
+    const int smem = 1024 + 2 * (2 * 16384 + 2 * p.kv_bytes) + 256;
+    static int smem_set = 0;
+    if (smem > smem_set)
+    {
+        CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    const int grid = p.n_problems < e->num_sms ? p.n_problems : e->num_sms;
+    attention_tc_kernel<<<grid, ATT_TC_THREADS, smem, s>>>(e->tmQ, e->tmKV, p);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
 int launch_attention(vitb200_engine *e, int B, cudaStream_t s)
 {
+    if (e->attn_tc) return launch_attention_tc(e, B, s);
     const int qtiles = (e->N + 15) / 16;
     if (qtiles <= 4) return launch_attention_t<4>(e, B, s);
     if (qtiles <= 14) return launch_attention_t<7>(e, B, s);
@@ -525,6 +551,17 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
         make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, B, D, D, GEMM_BM) ||
         make_tmap_f32_box32(&e->tmX, e->X, T, D, D))
         return bail(1);
+    {
+        const char *force = getenv("VITB200_ATTENTION"); // bring-up knob: "mma" forces the warp-MMA kernel
+        e->attn_tc = e->N <= 224 && !(force && strcmp(force, "mma") == 0);
+        if (e->attn_tc)
+        {
+            const int NKP = (e->N + 15) / 16 * 16;
+            if (make_tmap(&e->tmQ, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
+                make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP))
+                return bail(1);
+        }
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail("device sync after upload failed"));
     *out = e;
     return 0;

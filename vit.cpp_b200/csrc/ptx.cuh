@@ -126,6 +126,44 @@ __device__ __forceinline__ void tcgen05_ld_32x32b_x32(uint32_t taddr, uint32_t (
         : "memory");
 }
 __device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// thread i of the warp writes r[j] to lane (base_lane + i), column (base_col + j)
+__device__ __forceinline__ void tcgen05_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is an M x K f16 matrix held in TMEM, row m on lane m, two f16 per 32-bit
+// column (k = 2*col, 2*col+1) -- cute tmem_frg for M = 128.  A must be K-major.
+__device__ __forceinline__ void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 // UMMA shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, 64 f16 (=128 B) per row:
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for swizzled K-major)
@@ -140,9 +178,22 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Same for an MN-major operand (the MN dimension is contiguous in memory), SWIZZLE_128B, exactly one 64-element MN atom:
+// rows of 128 B are consecutive K indices; 8-row groups (1024 B) tile along K (stride byte offset); the leading byte
+// offset (distance between MN atoms) is irrelevant for a single atom and set to the tile size.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // UMMA instruction descriptor for kind::f16: c_format F32 (bit 4), a/b format (0 = f16, 1 = bf16) at bits 7 / 10,
 // a_major / b_major (0 = K-major, 1 = MN-major) at bits 15 / 16, N >> 3 at bits [17,23), M >> 4 at bits [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_fmt, int b_fmt, int a_mn_major = 0, int b_mn_major = 0)
+__host__ __device__ constexpr inline uint32_t umma_idesc_f16(int M, int N, int a_fmt, int b_fmt, int a_mn_major = 0, int b_mn_major = 0)
 {
     return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
