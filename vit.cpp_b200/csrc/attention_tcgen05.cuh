@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t att_exp_pair(float x0, float x1, float &lsum
 {
     // e = f16(exp(f32(f16(x))))  (ggml.c:10547-10549), two elements at a time
     const float2 xr = __half22float2(__floats2half2_rn(x0, x1));
-    const __half2 e = __floats2half2_rn(__expf(xr.x), __expf(xr.y));
+    const __half2 e = __floats2half2_rn(ptx::ex2_approx(xr.x * 1.4426950408889634f), ptx::ex2_approx(xr.y * 1.4426950408889634f));
     const float2 ef = __half22float2(e);
     lsum += ef.x + ef.y;
     return *reinterpret_cast<const uint32_t *>(&e);
@@ -123,28 +123,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint32_t idesc_s = ptx::umma_idesc_f16(128, p.NKP, 0, 0, 0, 0);
             const uint32_t idesc_o = ptx::umma_idesc_f16(128, 64, 0, 0, 0, /*B (V) is MN-major*/ 1);
             const int ksteps = p.NKP / 16;
+            // S_t = Q_t K^T of one problem (4 MMAs, K = 64)
+            auto issue_s = [&](int st, int t) {
+                const uint64_t kdesc = ptx::umma_desc_kmajor_sw128(sK(st));
+                const uint64_t qdesc = ptx::umma_desc_kmajor_sw128(sQ(st, t));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::tcgen05_mma_f16(tmem_base + scol[t], qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0);
+                ptx::tcgen05_commit(s_full(t));
+            };
             int i = 0;
-            for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
+            const int first = blockIdx.x;
+            if (first < p.n_problems)
+            {
+                ptx::mbar_wait(load_full(0), 0);
+                ptx::tcgen05_fence_after();
+                for (int t = 0; t < p.n_mtiles; ++t) issue_s(0, t);
+            }
+            for (int prob = first; prob < p.n_problems; prob += gridDim.x, ++i)
             {
                 const int st = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
-                ptx::mbar_wait(load_full(st), ph);
-                ptx::tcgen05_fence_after();
-                const uint64_t kdesc = ptx::umma_desc_kmajor_sw128(sK(st));
-                for (int t = 0; t < p.n_mtiles; ++t)
-                {
-                    // S_t = Q_t K^T.  The in-order tensor pipe runs this after P_t V of the previous problem, whose
-                    // p_ready wait guarantees the soft-max warps are done with the old S_t / P_t columns.
-                    const uint64_t qdesc = ptx::umma_desc_kmajor_sw128(sQ(st, t));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ptx::tcgen05_mma_f16(tmem_base + scol[t], qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0);
-                    ptx::tcgen05_commit(s_full(t));
-                }
+                const bool has_next = prob + (int)gridDim.x < p.n_problems;
                 const uint64_t vdesc = ptx::umma_desc_mnmajor_sw128(sV(st), (uint32_t)p.kv_bytes);
                 for (int t = 0; t < p.n_mtiles; ++t)
                 {
-                    ptx::mbar_wait(p_ready(t), i & 1); // P_t is in TMEM
+                    ptx::mbar_wait(p_ready(t), i & 1); // P_t is in TMEM (and the soft-max warps are done with S_t)
                     // the single O accumulator must have been drained by its previous user
                     if (t == 0) { if (i > 0) ptx::mbar_wait(o_empty(p.n_mtiles - 1), (i - 1) & 1); }
                     else ptx::mbar_wait(o_empty(0), i & 1);
@@ -152,8 +155,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     for (int j = 0; j < ksteps; ++j) // 16 keys per step: 8 TMEM columns of packed f16, 16 rows (2048 B) of V
                         ptx::tcgen05_mma_f16_ts(tmem_base + ATT_TC_OCOL, tmem_base + scol[t] + 8 * j, vdesc + (uint64_t)(j * 128), idesc_o, j > 0);
                     ptx::tcgen05_commit(o_full(t));
+                    if (t == p.n_mtiles - 1) ptx::tcgen05_commit(load_empty(st)); // all MMAs reading this smem stage have retired
+                    // S_t of the NEXT problem (other smem stage) goes into the pipe right behind P_t V: the in-order tensor
+                    // pipe runs it after P_t V has consumed the aliased P_t columns, so tile t's warpgroup finds its next
+                    // scores ready as soon as it has drained O
+                    if (has_next)
+                    {
+                        if (t == 0)
+                        {
+                            ptx::mbar_wait(load_full(st ^ 1), ((i + 1) >> 1) & 1);
+                            ptx::tcgen05_fence_after();
+                        }
+                        issue_s(st ^ 1, t);
+                    }
                 }
-                ptx::tcgen05_commit(load_empty(st)); // all MMAs reading this smem stage have retired
             }
         }
         __syncwarp();
@@ -215,20 +230,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         uint32_t v[32], pk[16];
                         ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, v);
                         ptx::tcgen05_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
+                        if (c * 32 + 32 <= p.N)
                         {
-                            const int key = c * 32 + 2 * j;
-                            float l2 = 0.f;
-                            uint32_t e = att_exp_pair(__fmaf_rn(__uint_as_float(v[2 * j]), p.scale, -mxs),
-                                                      __fmaf_rn(__uint_as_float(v[2 * j + 1]), p.scale, -mxs), l2);
-                            if (key + 1 >= p.N) // masked keys contribute exactly zero
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                pk[j] = att_exp_pair(__fmaf_rn(__uint_as_float(v[2 * j]), p.scale, -mxs),
+                                                     __fmaf_rn(__uint_as_float(v[2 * j + 1]), p.scale, -mxs), lsum);
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
                             {
-                                if (key >= p.N) { e = 0u; l2 = 0.f; }
-                                else { e &= 0xFFFFu; l2 = __half2float(__ushort_as_half((unsigned short)(e & 0xFFFFu))); }
+                                const int key = c * 32 + 2 * j;
+                                float l2 = 0.f;
+                                uint32_t e = att_exp_pair(__fmaf_rn(__uint_as_float(v[2 * j]), p.scale, -mxs),
+                                                          __fmaf_rn(__uint_as_float(v[2 * j + 1]), p.scale, -mxs), l2);
+                                if (key + 1 >= p.N) // masked keys contribute exactly zero
+                                {
+                                    if (key >= p.N) { e = 0u; l2 = 0.f; }
+                                    else { e &= 0xFFFFu; l2 = __half2float(__ushort_as_half((unsigned short)(e & 0xFFFFu))); }
+                                }
+                                pk[j] = e;
+                                lsum += l2;
                             }
-                            pk[j] = e;
-                            lsum += l2;
                         }
                         ptx::tcgen05_st_32x32b_x16(t_s + c * 16, pk);
                     }

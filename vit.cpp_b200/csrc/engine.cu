@@ -98,7 +98,7 @@ struct Linear
     __half *w = nullptr; // [n_out][ld] f16, K contiguous (ggml ne0 = K)
     float *b = nullptr;  // [n_out]
     int n_out = 0, n_in = 0, ld = 0, bn = 256;
-    CUtensorMap tm;
+    CUtensorMap tm;  // box = 64 x (bn / cta_group) rows: the share of the W tile one CTA stages
 };
 
 struct Layer
@@ -130,6 +130,7 @@ struct vitb200_engine
     bool attn_tc = false; // tcgen05 attention (N <= 224); longer sequences use the mma.sync two-pass kernel
     int max_k = 16;
     int launches = 0;
+    int cta_group = 2; // CTAs per tcgen05.mma in the GEMMs (2 = CTA pairs; VITB200_CTA_GROUP=1 selects the 1-CTA kernels)
     std::map<int, std::string> labels;
     // host-buffer pipeline (vitb200_forward_async): 2 input/output slots, H2D on a copy stream overlapping the previous
     // call's kernels on the compute stream
@@ -197,7 +198,7 @@ int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::
     CUDA_TRY(cudaMemset(L->w, 0, (size_t)n_out * ld * sizeof(__half)));
     CUDA_TRY(cudaMemcpy2D(L->w, (size_t)ld * 2, w->data, (size_t)n_in * 2, (size_t)n_in * 2, (size_t)n_out, cudaMemcpyHostToDevice));
     if (upload_f32(e, t, n, bname, n_out, &L->b)) return 1;
-    return make_tmap(&L->tm, L->w, (uint64_t)n_out, (uint64_t)ld, (uint64_t)ld, (uint32_t)L->bn);
+    return make_tmap(&L->tm, L->w, (uint64_t)n_out, (uint64_t)ld, (uint64_t)ld, (uint32_t)(L->bn / e->cta_group));
 }
 
 enum ProfKind { PK_PATCH = 0, PK_QKV, PK_PROJ, PK_FC1, PK_FC2, PK_HEAD, PK_ATTN, PK_LN, PK_COUNT };
@@ -226,30 +227,42 @@ struct ProfScope
     }
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
-    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32>;
-    auto kern = gemm_tcgen05_kernel<BN, EPI, 0>;
+    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, 0, CG>;
     static bool attr_set = false;
     if (!attr_set)
     {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG), n_tiles = (p.N + BN - 1) / BN;
     const int tiles = m_tiles * n_tiles;
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmX, p);
-    CUDA_TRY(cudaGetLastError());
+    const int max_groups = num_sms / CG;
+    const int groups = tiles < max_groups ? tiles : max_groups;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(groups * CG));
+    cfg.blockDim = dim3((unsigned)Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmX, p));
     if (e) e->launches++;
     return 0;
 }
 
-// tmX: f32 [M][ldo] map of the residual/output (EPI_BIAS_RESID_F32 only; ignored otherwise)
-int launch_gemm(vitb200_engine *e, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
+// tmB: box rows = bn / cg.  tmX: f32 [M][ldo] map of the residual/output (EPI_BIAS_RESID_F32 only; ignored otherwise)
+int launch_gemm(vitb200_engine *e, int cg, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
-#define VB_CASE(BN, EPI) if (bn == BN && epi == EPI) return launch_gemm_t<BN, EPI>(e, tmA, tmB, tmX, p, s, num_sms);
+#define VB_CASE(BN, EPI)                                                                                         \
+    if (bn == BN && epi == EPI)                                                                                  \
+        return cg == 2 ? launch_gemm_t<BN, EPI, 2>(e, tmA, tmB, tmX, p, s, num_sms) : launch_gemm_t<BN, EPI, 1>(e, tmA, tmB, tmX, p, s, num_sms);
     VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
     VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
     VB_CASE(256, EPI_BIAS_RESID_F32) VB_CASE(128, EPI_BIAS_RESID_F32)
@@ -383,7 +396,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         p.M = B * e->NP; p.N = D; p.K = e->KPp; p.bias = e->patch.b; p.out = e->X; p.ldo = D;
         p.pos = e->pos; p.np = e->NP; p.ntok = N;
         ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
-        if (launch_gemm(e, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
 
@@ -400,7 +413,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.ldo = 3 * D;
             ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
+            if (launch_gemm(e, e->cta_group, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
         }
         if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s)) return 1;
         {
@@ -412,7 +425,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = D; p.K = D; p.bias = L.proj.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_PROJ, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
+            if (launch_gemm(e, e->cta_group, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
         }
         if (tap && tap_f32(taps->x1, e->X, (size_t)T * D, s)) return 1;
         {
@@ -424,14 +437,14 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D;
             ProfScope ps(e, PK_FC1, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
+            if (launch_gemm(e, e->cta_group, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
         }
         if (tap && tap_f16(taps->h, e->H16, (size_t)T * 4 * D, s)) return 1;
         {
             GemmParams p{};
             p.M = T; p.N = D; p.K = 4 * D; p.bias = L.fc2.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_FC2, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
+            if (launch_gemm(e, e->cta_group, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
         }
         if (tap && tap_f32(taps->x2, e->X, (size_t)T * D, s)) return 1;
     }
@@ -445,7 +458,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         GemmParams p{};
         p.M = B; p.N = C; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = C;
         ProfScope ps(e, PK_HEAD, 2.0 * p.M * p.N * p.K, s);
-        if (launch_gemm(e, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, e->tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (d_probs || (k > 0 && (d_topk_idx || d_topk_val)))
     {
@@ -493,6 +506,7 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
     e->N = e->NP + 1;
     e->KP = 3 * P * P;
     e->KPp = (e->KP + 63) / 64 * 64;
+    e->cta_group = (getenv("VITB200_CTA_GROUP") && atoi(getenv("VITB200_CTA_GROUP")) == 1) ? 1 : 2;
     auto bail = [&](int) { vitb200_destroy(e); return 1; };
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
 
@@ -726,8 +740,9 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
             cudaMemcpy(dR, resid, (size_t)M * N * 4, cudaMemcpyHostToDevice);
         }
         const int bn = pick_bn(N);
+        const int cg = (getenv("VITB200_CTA_GROUP") && atoi(getenv("VITB200_CTA_GROUP")) == 1) ? 1 : 2;
         CUtensorMap tA, tB, tX;
-        if (make_tmap(&tA, dA, M, K, K, GEMM_BM) || make_tmap(&tB, dW, N, K, K, bn)) break;
+        if (make_tmap(&tA, dA, M, K, K, GEMM_BM) || make_tmap(&tB, dW, N, K, K, bn / cg)) break;
         memset(&tX, 0, sizeof(tX));
         if (epilogue == EPI_BIAS_RESID_F32)
         {
@@ -737,7 +752,7 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
         }
         GemmParams p{};
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.ldo = N; p.resid = (const float *)dO;
-        if (launch_gemm(nullptr, bn, epilogue, tA, tB, tX, p, 0, prop.multiProcessorCount)) break;
+        if (launch_gemm(nullptr, cg, bn, epilogue, tA, tB, tX, p, 0, prop.multiProcessorCount)) break;
         cudaError_t err = cudaDeviceSynchronize();
         if (err != cudaSuccess) { fail("GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
         if (f16out)

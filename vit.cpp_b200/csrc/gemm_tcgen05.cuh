@@ -44,7 +44,10 @@ constexpr int GEMM_BK = 64;
 // The residual epilogue (proj, fc2) streams the f32 residual tile through a per-warp TMA ring (kResidRing slots of
 // 32 rows x 32 columns = 4 KB) and stores the result with TMA from the same slot, so ~64 KB of residual loads are in
 // flight per SM without holding registers; it pays for the ring with one fewer operand stage.
-template <int BN, bool kResid>
+// CG = CTAs per MMA (cta_group): 2 = a CTA pair on one TPC computes a 256 x BN tile with M = 256 tcgen05.mma; each CTA
+// stages its own 128 A rows and HALF of the W tile (the pair shares both halves), which halves the per-SM shared-memory
+// traffic of the B operand -- the 1-CTA kernel is shared-memory-bandwidth bound at ~70 % tensor-pipe utilisation.
+template <int BN, bool kResid, int CG>
 struct GemmCfg
 {
     static constexpr int kResidRing = 5;
@@ -52,33 +55,39 @@ struct GemmCfg
     // the columns) so the ALU-heavy f16 epilogues (bias, GELU, packing) have two warps per SM sub-partition to overlap
     static constexpr int kEpiWarps = kResid ? 4 : 8;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
-    static constexpr int kStages = kResid ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 4 : 6);
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int B_ROWS = BN / CG;               // W rows staged by this CTA
+    static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = kResid ? 4 * kResidRing * 4096 : kEpiWarps * 4096; // per epilogue warp: ring or transpose buffer
     static constexpr int BAR_BYTES = 512;
+    static constexpr int kSmemLimit = 232448; // 227 KB per CTA
+    static constexpr int kStagesFit = (kSmemLimit - 1024 - STAGE_BYTES - BAR_BYTES) / (A_BYTES + B_BYTES);
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit; // operand ring depth: whatever fits
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * (A_BYTES + B_BYTES) + STAGE_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
-// GELU, tanh form, exactly the reference's formula (ggml.c:1418-1424) evaluated in f32 on an f16-valued
-// input; tanh via 1 - 2/(1+e^{2u}).  The result is rounded to f16 by the caller (ggml.c:2197 table semantics).
+// GELU, tanh form (the reference's formula, ggml.c:1418-1424) on an f16-valued input, evaluated in f32 as
+//   0.5 x (1 + tanh(u)) = x / (1 + e^{-2u}),   u = sqrt(2/pi) x (1 + 0.044715 x^2)
+// (algebraically identical; 6 FMA-pipe ops + MUFU.EX2 + MUFU.RCP, relative error ~3e-7, i.e. the f16 rounding the caller
+// applies next (table semantics, ggml.c:2197) differs from the host table in well under 0.1 % of inputs, by one ulp).
 __device__ __forceinline__ float gelu_tanh_f32(float x)
 {
-    const float u = 0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x);
-    const float e = __expf(2.0f * u);
-    const float t = 1.0f - __fdividef(2.0f, 1.0f + e);
-    return 0.5f * x * (1.0f + t);
+    const float inner = fmaf(0.044715f * x, x, 1.0f);
+    const float t = x * inner;                                   // u / sqrt(2/pi)
+    const float e = ptx::ex2_approx(t * -2.3022081981625516f);   // e^{-2u}: -2 * sqrt(2/pi) * log2(e)
+    return x * ptx::rcp_approx(1.0f + e);
 }
 
-template <int BN, int EPI, int B_FMT>
-__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32>::kThreads), 1)
+template <int BN, int EPI, int B_FMT, int CG>
+__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG>::kThreads), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const GemmParams p)
 {
     constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32);
-    using Cfg = GemmCfg<BN, kResid>;
+    using Cfg = GemmCfg<BN, kResid, CG>;
+    constexpr int TILE_M = GEMM_BM * CG; // rows of C per CTA group
     constexpr int kStages = Cfg::kStages;
     constexpr bool kOutF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
 
@@ -102,10 +111,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u; // 0 = leader of the pair
+    const int group_id = blockIdx.x / CG, num_groups = gridDim.x / CG;  // persistent tile loop runs per CTA group
+    if constexpr (CG == 2) ptx::cluster_sync(); // both CTAs resident before the pair-wide TMEM allocation
 
     if (warp_idx == 0 && lane == 0)
     {
@@ -117,13 +129,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
         for (int s = 0; s < kStages; ++s)
         {
-            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(full_bar(s), CG); // one (remote) arrival per producer of the pair; leader's barrier collects all bytes
             ptx::mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a)
         {
             ptx::mbar_init(tfull_bar(a), 1);
-            ptx::mbar_init(tempty_bar(a), Cfg::kEpiWarps); // one arrival per epilogue warp
+            ptx::mbar_init(tempty_bar(a), CG * Cfg::kEpiWarps); // one arrival per epilogue warp of the group (leader's barrier)
         }
         if constexpr (kResid)
             for (int w = 0; w < 4; ++w)
@@ -132,11 +144,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp_idx == 2)
     {
-        ptx::tcgen05_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
-        ptx::tcgen05_relinquish();
+        if constexpr (CG == 2) { ptx::tcgen05_alloc_cg2(tmem_ptr_addr, Cfg::TMEM_COLS); ptx::tcgen05_relinquish_cg2(); }
+        else { ptx::tcgen05_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); ptx::tcgen05_relinquish(); }
     }
     ptx::tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads(); // barrier inits visible to the peer before any remote arrive
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -147,15 +159,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (int tile = group_id; tile < num_tiles; tile += num_groups)
             {
                 const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                const int a_row = m_blk * TILE_M + (int)cta_rank * GEMM_BM;   // this CTA's 128 rows of A
+                const int b_row = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;   // this CTA's share of the W tile
                 for (int kb = 0; kb < num_kb; ++kb)
                 {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
-                    ptx::tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * GEMM_BM);
-                    ptx::tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN);
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1); // own slot free (the MMA commit is multicast to both CTAs)
+                    if constexpr (CG == 2)
+                    {
+                        // all bytes of the pair are accounted on the LEADER's full barrier
+                        if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+                        else ptx::mbar_arrive_remote(full_bar(stage), 0);
+                        ptx::tma_load_2d_cg2(sA + stage * Cfg::A_BYTES, &tmA, full_bar(stage), kb * GEMM_BK, a_row);
+                        ptx::tma_load_2d_cg2(sB + stage * Cfg::B_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, b_row);
+                    }
+                    else
+                    {
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
+                        ptx::tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, full_bar(stage), kb * GEMM_BK, a_row);
+                        ptx::tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, b_row);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -165,13 +190,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     else if (warp_idx == 1)
     {
         // ===================== MMA issuer (single thread) =====================
-        if (lane == 0)
+        if (lane == 0 && cta_rank == 0) // the leader CTA issues for the whole group
         {
-            constexpr uint32_t idesc = ptx::umma_idesc_f16(GEMM_BM, BN, /*a=f16*/ 0, B_FMT);
+            constexpr uint32_t idesc = ptx::umma_idesc_f16(TILE_M, BN, /*a=f16*/ 0, B_FMT);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+            for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it)
             {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -188,10 +213,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int k = 0; k < GEMM_BK / 16; ++k)
                     {
                         // advance 16 f16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-                        ptx::tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (CG == 2) ptx::tcgen05_mma_f16_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else ptx::tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    ptx::tcgen05_commit(empty_bar(stage)); // frees the smem slot when these MMAs retire
-                    if (kb == num_kb - 1) ptx::tcgen05_commit(tfull_bar(as)); // accumulator complete
+                    if constexpr (CG == 2)
+                    {
+                        ptx::tcgen05_commit_cg2(empty_bar(stage), 3); // frees the slot in BOTH CTAs when these MMAs retire
+                        if (kb == num_kb - 1) ptx::tcgen05_commit_cg2(tfull_bar(as), 3); // accumulator complete, both epilogues
+                    }
+                    else
+                    {
+                        ptx::tcgen05_commit(empty_bar(stage)); // frees the smem slot when these MMAs retire
+                        if (kb == num_kb - 1) ptx::tcgen05_commit(tfull_bar(as)); // accumulator complete
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -217,28 +251,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t ring_u32 = ptx::smem_u32(ring);
             auto n_chunks_of = [&](int tile) { const int n0 = (tile % n_tiles) * BN; const int rem = p.N - n0; return (rem >= BN ? BN : rem + 31) / 32; };
             // prefetch cursor
-            int pf_tile = blockIdx.x, pf_chunk = 0, pf_count = 0;
+            int pf_tile = group_id, pf_chunk = 0, pf_count = 0;
             auto issue_next = [&]() {
                 if (pf_tile >= num_tiles) return;
                 const int slot = pf_count % R;
-                const int row0 = (pf_tile / n_tiles) * GEMM_BM + q * 32;
+                const int row0 = (pf_tile / n_tiles) * TILE_M + (int)cta_rank * GEMM_BM + q * 32;
                 const int col0 = (pf_tile % n_tiles) * BN + pf_chunk * 32;
                 ptx::mbar_arrive_expect_tx(rfull_bar(ew, slot), 4096);
                 ptx::tma_load_2d(ring_u32 + slot * 4096, &tmX, rfull_bar(ew, slot), col0, row0);
                 ++pf_count;
-                if (++pf_chunk == n_chunks_of(pf_tile)) { pf_chunk = 0; pf_tile += gridDim.x; }
+                if (++pf_chunk == n_chunks_of(pf_tile)) { pf_chunk = 0; pf_tile += num_groups; }
             };
             if (lane == 0)
                 for (int i = 0; i < R - 1; ++i) issue_next();
             int cons = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+            for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it)
             {
                 const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 ptx::mbar_wait(tfull_bar(as), aphase);
                 ptx::tcgen05_fence_after();
-                const int m0 = m_blk * GEMM_BM + q * 32;
+                const int m0 = m_blk * TILE_M + (int)cta_rank * GEMM_BM + q * 32;
                 const int n0 = n_blk * BN;
                 const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
                 const int nch = n_chunks_of(tile);
@@ -252,7 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     {
                         ptx::tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+                        if (lane == 0) { if (cta_rank == 0) ptx::mbar_arrive(tempty_bar(as)); else ptx::mbar_arrive_remote(tempty_bar(as), 0); }
                     }
                     const int slot = cons % R;
                     ptx::mbar_wait(rfull_bar(ew, slot), (cons / R) & 1);
@@ -290,14 +324,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         {
         uint8_t *stg = stg_base + (warp_idx - 2) * 4096;
         const int half_sel = (warp_idx - 2) >> 2; // warps w and w+4 share a TMEM lane quarter and alternate column passes
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+        for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it)
         {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tcgen05_fence_after();
-            const int m0 = m_blk * GEMM_BM + q * 32;
+            const int m0 = m_blk * TILE_M + (int)cta_rank * GEMM_BM + q * 32;
             const int n0 = n_blk * BN;
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 
@@ -324,7 +358,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // this warp's last TMEM read of this accumulator: hand it back to the MMA warp early
                     ptx::tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+                    if (lane == 0) { if (cta_rank == 0) ptx::mbar_arrive(tempty_bar(as)); else ptx::mbar_arrive_remote(tempty_bar(as), 0); }
                 }
 
                 if constexpr (kOutF16)
@@ -424,11 +458,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     // ===================== teardown =====================
     ptx::tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads(); // the peer may still be reading its TMEM / signalling our barriers
     if (warp_idx == 2)
     {
         ptx::tcgen05_fence_after();
-        ptx::tcgen05_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (CG == 2) ptx::tcgen05_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+        else ptx::tcgen05_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

@@ -134,7 +134,7 @@ __global__ void layernorm_f16_kernel(const float *__restrict__ x, size_t x_row_s
 __device__ __forceinline__ __half exp_f16_semantics(float x)
 {
     const float xr = __half2float(__float2half_rn(x));
-    return __float2half_rn(__expf(xr));
+    return __float2half_rn(ptx::ex2_approx(xr * 1.4426950408889634f));
 }
 
 // ------------------------------------------------------------------------------------------------
