@@ -33,7 +33,8 @@ typedef struct vitb200_hparams
     int32_t num_classes;
     int32_t patch_size;
     int32_t img_size;
-    int32_t ftype; /* 0 f32, 1 f16, 8 q8_0 (reference vit.cpp:385-414); 1 is implemented, others are rejected */
+    int32_t ftype; /* 0 f32, 1 f16, 8 q8_0 (reference vit.cpp:385-414).  f16 is the native path; q8_0 and f32 weights are
+                    * converted to f16 once at upload; other quant formats are rejected */
     float eps;     /* layer-norm epsilon, 1e-6 in the reference (vit.h:29) */
 } vitb200_hparams;
 

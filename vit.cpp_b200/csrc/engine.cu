@@ -184,19 +184,54 @@ int upload_f32(vitb200_engine *e, const vitb200_tensor *t, int n, const std::str
     return 0;
 }
 
-// f16 matrix [n_out][n_in] -> device, row pitch padded to ld (zero filled), + its TMA descriptor
+// IEEE f32 -> f16 round-to-nearest-even on the host (upload-time conversions only)
+uint16_t host_f32_to_f16(float f) { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+float host_f16_to_f32(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
+
+// Weight matrix [n_out][n_in] -> device f16, row pitch padded to ld (zero filled), + its TMA descriptor.
+//   type 1 (F16): used as stored -- the reference's own operand (ggml.c:1200-1236).
+//   type 8 (Q8_0, blocks of {f16 d; int8 q[32]}, ggml-quants.h:42-46): dequantised once to f16(d * q).  The reference
+//          multiplies int8 x dynamically quantised int8 activations (ggml-quants.c:3521); this W8A16 form stays within the
+//          q8_0 noise floor of that path (1.6e-2 either way); an int8 tensor-core path is future work.
+//   type 0 (F32): rounded once to f16 (the reference keeps f32 weights AND f32 activations, ggml.c:1163-1198).
 int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &wname, const std::string &bname,
                   int n_out, int n_in, int ld, Linear *L)
 {
     const vitb200_tensor *w = find_tensor(t, n, wname);
     if (!w) return fail("missing tensor '%s'", wname.c_str());
-    if (w->type != 1)
-        return fail("tensor '%s': weight type %d is not supported by this build (f16 model files only)", wname.c_str(), w->type);
+    if (w->type != 0 && w->type != 1 && w->type != 8)
+        return fail("tensor '%s': weight type %d is not supported (f32, f16, q8_0 only)", wname.c_str(), w->type);
     if (nelem(w) != (int64_t)n_out * n_in) return fail("tensor '%s' has wrong size: got %lld, expected %lld", wname.c_str(), (long long)nelem(w), (long long)n_out * n_in);
+    if (w->type == 8 && n_in % 32 != 0) return fail("tensor '%s': q8_0 rows must be a multiple of 32", wname.c_str());
     L->n_out = n_out; L->n_in = n_in; L->ld = ld; L->bn = pick_bn(n_out);
     if (dev_alloc(e, &L->w, (size_t)n_out * ld)) return 1;
     CUDA_TRY(cudaMemset(L->w, 0, (size_t)n_out * ld * sizeof(__half)));
-    CUDA_TRY(cudaMemcpy2D(L->w, (size_t)ld * 2, w->data, (size_t)n_in * 2, (size_t)n_in * 2, (size_t)n_out, cudaMemcpyHostToDevice));
+    const void *src = w->data;
+    std::vector<uint16_t> conv;
+    if (w->type != 1)
+    {
+        conv.resize((size_t)n_out * n_in);
+        if (w->type == 0)
+        {
+            const float *f = (const float *)w->data;
+            for (size_t i = 0; i < conv.size(); ++i) conv[i] = host_f32_to_f16(f[i]);
+        }
+        else
+        {
+            const uint8_t *blk = (const uint8_t *)w->data;
+            const size_t nb = conv.size() / 32;
+            for (size_t b = 0; b < nb; ++b)
+            {
+                uint16_t du;
+                memcpy(&du, blk + b * 34, 2);
+                const float d = host_f16_to_f32(du);
+                const int8_t *q = (const int8_t *)(blk + b * 34 + 2);
+                for (int i = 0; i < 32; ++i) conv[b * 32 + i] = host_f32_to_f16(d * (float)q[i]);
+            }
+        }
+        src = conv.data();
+    }
+    CUDA_TRY(cudaMemcpy2D(L->w, (size_t)ld * 2, src, (size_t)n_in * 2, (size_t)n_in * 2, (size_t)n_out, cudaMemcpyHostToDevice));
     if (upload_f32(e, t, n, bname, n_out, &L->b)) return 1;
     return make_tmap(&L->tm, L->w, (uint64_t)n_out, (uint64_t)ld, (uint64_t)ld, (uint32_t)(L->bn / e->cta_group));
 }

@@ -66,13 +66,16 @@ __device__ __forceinline__ void cluster_sync()
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Deliberately WITHOUT
+// .release.cluster: that form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, which drains every outstanding
+// TMA load of the producer and collapsed the CTA-pair pipeline to depth 1 (ncu: 32 % tensor-pipe, profiles/).  The data these
+// arrivals order is tracked elsewhere (TMA transaction bytes; tcgen05.fence::before_thread_sync for TMEM reads).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta)
 {
     asm volatile(
         "{\n\t.reg .b32 r;\n\t"
         "mapa.shared::cluster.u32 r, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}"
         ::"r"(bar), "r"(cta)
         : "memory");
 }
