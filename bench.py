@@ -36,6 +36,13 @@ MODEL_CFG = "base"
 FLOPS_PER_IMAGE = 35.128e9  # BASELINE.md section 3 / SURVEY.md 8(d): 2 * 17.564 GMAC, ViT-B/16 224^2
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each GEMM of the step, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/summarize_ncu.py); None when no capture exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -114,7 +121,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     nproc = host_threads()
-    cand = sorted({min(nproc, 64), max(1, min(nproc, 64) // 2)}, reverse=True)
+    cand = sorted({min(nproc, 64), max(1, min(nproc, 64) // 2), max(1, min(nproc, 64) // 4)}, reverse=True)
     per_step = 4
     # choose the better thread count on a short probe, then time exactly `steps` steps of `per_step` images
     rate, nt, _ = cpu_reference_rate(2, cand)
@@ -208,11 +215,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-data throughput -------------------------------------------------------------------
-    for i in range(W):
+    # ---- resident-data throughput (region A: the product path, kernel schedule replayed as a CUDA graph) --------
+    for i in range(W + 2):  # first two calls per input buffer run eagerly / capture the graph
         step_device(i)
     sync_all()
-    L.vitb200_profile_enable(model.handle, 1)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,6 +230,15 @@ def main():
     ms_local = e0.elapsed_time(e1)
     clocks = sampler.result()
     launches_per_step = model.last_launch_count()
+    # ---- region B: the same K steps launched eagerly with CUDA-event pairs around every tracked kernel (roofline) --------
+    L.vitb200_profile_enable(model.handle, 1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(args.steps):
+        step_device(i)
+    p1.record()
+    torch.cuda.synchronize()
+    ms_profiled = p0.elapsed_time(p1)
     prof = {}
     for kind, name in enumerate(["patch", "qkv", "proj", "fc1", "fc2", "head", "attention", "layernorm"]):
         ms, cnt, fl = C.c_double(), C.c_int(), C.c_double()
@@ -279,8 +294,11 @@ def main():
             avg_s = d["ms_total"] * 1e-3 / d["launches"]
             ach = d["flops_per_launch"] / avg_s / 1e12
             roof = {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel ({dom})", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["which"],
-                    "avg_launch_ms": avg_s * 1e3, "share_of_step": d["ms_total"] / ms_local}
+                    "frac": ach / peaks["tflops"], "traffic": ncu_traffic().get(dom), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                    "peak_source": peaks["which"],
+                    "avg_launch_ms": avg_s * 1e3, "share_of_step": d["ms_total"] / ms_profiled,
+                    "timed_in": "a second pass of the same %d steps, launched eagerly with a CUDA-event pair around every tracked kernel "
+                                "(%.3f ms/step vs %.3f ms/step for the graph-replayed pass that `value` reports)" % (args.steps, ms_profiled / args.steps, ms_local / args.steps)}
         line = {
             "metric": "images/sec ViT-B/16 224^2 forward", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -302,7 +320,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             nproc = host_threads()
-            cand = sorted({min(nproc, 64), max(1, min(nproc, 64) // 2)}, reverse=True)
+            cand = sorted({min(nproc, 64), max(1, min(nproc, 64) // 2), max(1, min(nproc, 64) // 4)}, reverse=True)
             rate, nt, dt = cpu_reference_rate(8, cand)
             line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": nt, "kind": "reference",
                                     "sample": "8 images of the same ViT-B/16 f16 model through oracle/_ref vit_predict (%.1f s), host has %d cores" % (dt, nproc)}

@@ -197,18 +197,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 {
                     // ---- pass 1: true row maximum over the valid keys (ggml.c:10533-10534)
                     float mx = -INFINITY;
-                    for (int c = 0; c < n32; ++c)
                     {
-                        uint32_t v[32];
-                        ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, v);
-                        ptx::tcgen05_wait_ld();
-                        if (c * 32 + 32 <= p.N)
+                        float ma = -INFINITY, mb = -INFINITY;
+                        int c = 0;
+                        for (; c + 2 <= (p.N >> 5); c += 2) // two mask-free chunks per iteration
                         {
+                            uint32_t va[32], vb[32];
+                            ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, va);
+                            ptx::tcgen05_ld_32x32b_x32(t_s + c * 32 + 32, vb);
+                            ptx::tcgen05_wait_ld();
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                            for (int j = 0; j < 32; ++j) { ma = fmaxf(ma, __uint_as_float(va[j])); mb = fmaxf(mb, __uint_as_float(vb[j])); }
                         }
-                        else
+                        mx = fmaxf(ma, mb);
+                        for (; c < n32; ++c)
                         {
+                            uint32_t v[32];
+                            ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, v);
+                            ptx::tcgen05_wait_ld();
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (c * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
@@ -224,8 +230,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             if (n32 * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
                     }
                     const float mxs = mx * p.scale; // ggml_scale_inplace (vit.cpp:851-854); exact, scale = 1/8
-                    // ---- pass 2: P = f16(exp(f16(s*scale - max))) -> packed f16 into the S columns, l = sum P
-                    for (int c = 0; c < n32; ++c)
+                    // ---- pass 2: P = f16(exp(f16(s*scale - max))) -> packed f16 into the S columns, l = sum P.
+                    // Full (mask-free) chunks go two at a time with four independent partial sums so one warp keeps the
+                    // MUFU / conversion latencies overlapped; the chunk(s) straddling N take the masked path.
+                    const int n_full = p.N >> 5; // chunks with all 32 keys valid
+                    float l0 = 0.f, l1 = 0.f, l2s = 0.f, l3 = 0.f;
+                    int c = 0;
+                    for (; c + 2 <= n_full; c += 2)
+                    {
+                        uint32_t va[32], vb[32], pa[16], pb[16];
+                        ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, va);
+                        ptx::tcgen05_ld_32x32b_x32(t_s + c * 32 + 32, vb);
+                        ptx::tcgen05_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                        {
+                            pa[j] = att_exp_pair(__fmaf_rn(__uint_as_float(va[2 * j]), p.scale, -mxs), __fmaf_rn(__uint_as_float(va[2 * j + 1]), p.scale, -mxs), l0);
+                            pb[j] = att_exp_pair(__fmaf_rn(__uint_as_float(vb[2 * j]), p.scale, -mxs), __fmaf_rn(__uint_as_float(vb[2 * j + 1]), p.scale, -mxs), l1);
+                            pa[j + 1] = att_exp_pair(__fmaf_rn(__uint_as_float(va[2 * j + 2]), p.scale, -mxs), __fmaf_rn(__uint_as_float(va[2 * j + 3]), p.scale, -mxs), l2s);
+                            pb[j + 1] = att_exp_pair(__fmaf_rn(__uint_as_float(vb[2 * j + 2]), p.scale, -mxs), __fmaf_rn(__uint_as_float(vb[2 * j + 3]), p.scale, -mxs), l3);
+                        }
+                        ptx::tcgen05_st_32x32b_x16(t_s + c * 16, pa);
+                        ptx::tcgen05_st_32x32b_x16(t_s + c * 16 + 16, pb);
+                    }
+                    lsum = (l0 + l1) + (l2s + l3);
+                    for (; c < n32; ++c)
                     {
                         uint32_t v[32], pk[16];
                         ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, v);

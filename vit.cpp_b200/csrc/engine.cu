@@ -140,6 +140,10 @@ struct vitb200_engine
     int32_t *d_topk_idx_slot[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     unsigned long long submits = 0;
+    // CUDA-graph cache for the kernel schedule of one forward, keyed by its arguments (launch-bound inner loop: ~90 kernels)
+    struct GraphEntry { const void *img; int batch; void *probs, *logits, *tidx, *tval; int k; int state; int launches; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;
+    bool use_graph = true;
     // optional per-kernel timing (bench.py roofline): CUDA event pairs around tracked launches
     bool profile = false;
     struct ProfRec { int kind; cudaEvent_t a, b; double flops; };
@@ -504,6 +508,53 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     return 0;
 }
 
+// run_forward through a cached CUDA graph: the first call with a given argument set runs eagerly (also sets the kernels'
+// function attributes), the second captures + instantiates, later ones replay.  Profiling / taps always run eagerly.
+int run_forward_graphed(vitb200_engine *e, const float *d_images, int B, float *d_probs, float *d_logits, int32_t *d_topk_idx,
+                        float *d_topk_val, int k, cudaStream_t s)
+{
+    if (!e->use_graph || e->profile) return run_forward(e, d_images, B, d_probs, d_logits, d_topk_idx, d_topk_val, k, s, nullptr);
+    vitb200_engine::GraphEntry *g = nullptr;
+    for (auto &x : e->graphs)
+        if (x.img == d_images && x.batch == B && x.probs == d_probs && x.logits == d_logits && x.tidx == d_topk_idx && x.tval == d_topk_val && x.k == k) { g = &x; break; }
+    if (!g)
+    {
+        if (e->graphs.size() >= 16) { if (e->graphs.front().exec) cudaGraphExecDestroy(e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
+        e->graphs.push_back({d_images, B, d_probs, d_logits, d_topk_idx, d_topk_val, k, 0, 0, nullptr});
+        g = &e->graphs.back();
+    }
+    if (g->state == 0)
+    {
+        if (run_forward(e, d_images, B, d_probs, d_logits, d_topk_idx, d_topk_val, k, s, nullptr)) return 1;
+        g->state = 1;
+        g->launches = e->launches;
+        return 0;
+    }
+    if (g->state == 1)
+    {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_forward(e, d_images, B, d_probs, d_logits, d_topk_idx, d_topk_val, k, s, nullptr);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc != 0 || ce != cudaSuccess || !graph)
+        {
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+            g->state = 0;
+            e->use_graph = false; // fall back to eager launches (same kernels, same results)
+            return run_forward(e, d_images, B, d_probs, d_logits, d_topk_idx, d_topk_val, k, s, nullptr);
+        }
+        g->launches = e->launches;
+        ce = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { g->exec = nullptr; g->state = 0; e->use_graph = false; return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+        g->state = 2;
+    }
+    CUDA_TRY(cudaGraphLaunch(g->exec, s));
+    e->launches = g->launches;
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -542,6 +593,7 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
     e->KP = 3 * P * P;
     e->KPp = (e->KP + 63) / 64 * 64;
     e->cta_group = (getenv("VITB200_CTA_GROUP") && atoi(getenv("VITB200_CTA_GROUP")) == 1) ? 1 : 2;
+    e->use_graph = !(getenv("VITB200_GRAPH") && atoi(getenv("VITB200_GRAPH")) == 0);
     auto bail = [&](int) { vitb200_destroy(e); return 1; };
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
 
@@ -621,6 +673,7 @@ void vitb200_destroy(vitb200_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (void *p : e->allocs) cudaFree(p);
+    for (auto &g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -682,7 +735,9 @@ int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, 
     if (!e || !d_images) return fail("null argument");
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-    return run_forward(e, d_images, batch, d_probs, d_logits, d_topk_idx, d_topk_prob, k, s, nullptr);
+    if (batch < 1 || batch > e->max_batch) return fail("batch %d out of range (1..%d)", batch, e->max_batch);
+    if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
+    return run_forward_graphed(e, d_images, batch, d_probs, d_logits, d_topk_idx, d_topk_prob, k, s);
 }
 
 // Enqueue one batched forward with HOST buffers.  Slot s = call parity: the H2D of this call runs on the copy stream and
@@ -702,8 +757,13 @@ static int forward_enqueue(vitb200_engine *e, const float *images, int batch, fl
     CUDA_TRY(cudaEventRecord(e->ev_h2d[sl], cs));
     CUDA_TRY(cudaStreamWaitEvent(s, e->ev_h2d[sl], 0));
     const bool want_topk = k > 0 && (topk_idx || topk_prob);
-    if (run_forward(e, e->d_img_slot[sl], batch, (probs || want_topk) ? e->d_probs_slot[sl] : nullptr, e->d_logits_slot[sl],
-                    want_topk ? e->d_topk_idx_slot[sl] : nullptr, want_topk ? e->d_topk_val_slot[sl] : nullptr, want_topk ? k : 0, s, taps))
+    if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
+    float *dp = (probs || want_topk) ? e->d_probs_slot[sl] : nullptr;
+    int32_t *di = want_topk ? e->d_topk_idx_slot[sl] : nullptr;
+    float *dv = want_topk ? e->d_topk_val_slot[sl] : nullptr;
+    const int kk = want_topk ? k : 0;
+    if (taps ? run_forward(e, e->d_img_slot[sl], batch, dp, e->d_logits_slot[sl], di, dv, kk, s, taps)
+             : run_forward_graphed(e, e->d_img_slot[sl], batch, dp, e->d_logits_slot[sl], di, dv, kk, s))
         return 1;
     if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs_slot[sl], (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits_slot[sl], (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
