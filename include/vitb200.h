@@ -126,8 +126,7 @@ int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, flo
                           const vitb200_taps *taps);
 
 /* Stand-alone run of the tcgen05 GEMM kernel: out[M][N] = epilogue(A[M][K] (f16 bits) x W[N][K]^T (f16 bits)).
- * epilogue: 0 bias->f16, 1 bias+gelu->f16, 2 bias+resid->f32, 4 bias->f32; OR 0x100 when W holds bf16 bit patterns
- * (f16 activations x bf16 weights).  out is float32[M][N] on the host
+ * epilogue: 0 bias->f16, 1 bias+gelu->f16, 2 bias+resid->f32, 4 bias->f32.  out is float32[M][N] on the host
  * (f16 results widened).  resid may be NULL unless epilogue == 2. */
 int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W,
                       const float *bias, const float *resid, float *out);

@@ -67,16 +67,3 @@ def test_gemm_linearity_at_full_size():
     for r in (0, 127, 128, 25000, M - 1):
         assert np.array_equal(o1[r].astype(np.int64), A[r].astype(np.int64) @ W1.astype(np.int64).T)
 
-
-def test_gemm_f16_activations_times_bf16_weights():
-    """kind::f16 tcgen05.mma with a_format = f16 and b_format = bf16 in ONE instruction (the bf16-weight configuration)."""
-    M, N, K = 300, 768, 256
-    rng = np.random.default_rng(3)
-    A = rng.standard_normal((M, K)).astype(np.float16)
-    Wf = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
-    Wb = ((Wf.view(np.uint32) + 0x8000) >> 16).astype(np.uint16)  # round to bf16 (ties away: fine for a test)
-    Wref = (Wb.astype(np.uint32) << 16).view(np.float32)
-    bias = rng.standard_normal(N).astype(np.float32)
-    out = eng.test_gemm(M, N, K, 4 | 0x100, A, Wb.view(np.float16), bias)
-    ref = (A.astype(np.float64) @ Wref.astype(np.float64).T + bias).astype(np.float32)
-    np.testing.assert_allclose(out, ref, rtol=0, atol=2e-5 * max(1.0, np.abs(ref).max()))

@@ -98,7 +98,6 @@ struct Linear
     __half *w = nullptr; // [n_out][ld] f16, K contiguous (ggml ne0 = K)
     float *b = nullptr;  // [n_out]
     int n_out = 0, n_in = 0, ld = 0, bn = 256;
-    int bfmt = 0; // UMMA B-operand format of the stored weights: 0 = f16, 1 = bf16
     CUtensorMap tm;  // box = 64 x (bn / cta_group) rows: the share of the W tile one CTA stages
 };
 
@@ -218,22 +217,12 @@ int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::
         conv.resize((size_t)n_out * n_in);
         if (w->type == 0)
         {
-            // f32 file whose weights are exactly bf16-representable (a bf16 checkpoint widened to f32, the only way the
-            // legacy container can carry bf16: BASELINE.json configs[2]) -> keep them bit-exact as bf16 and run the
-            // f16-activation x bf16-weight tcgen05.mma; otherwise round once to f16.
-            const uint32_t *u = (const uint32_t *)w->data;
-            bool all_bf16 = true;
-            for (size_t i = 0; i < conv.size() && all_bf16; ++i) all_bf16 = (u[i] & 0xFFFFu) == 0;
-            if (all_bf16)
-            {
-                for (size_t i = 0; i < conv.size(); ++i) conv[i] = (uint16_t)(u[i] >> 16);
-                L->bfmt = 1;
-            }
-            else
-            {
-                const float *f = (const float *)w->data;
-                for (size_t i = 0; i < conv.size(); ++i) conv[i] = host_f32_to_f16(f[i]);
-            }
+            // Rounded once to f16.  A bf16 checkpoint widened to f32 (the only way this container can carry bf16,
+            // BASELINE.json configs[2]) converts EXACTLY for every weight with |w| >= 2^-14 (8-bit mantissa fits in 11).
+            // Keeping such weights as bf16 is not an option: tcgen05.mma kind::f16 with a_format = f16 and b_format = bf16
+            // raises "illegal instruction" on B200 (tried in round 1), and bf16 activations cost 5e-3 parity.
+            const float *f = (const float *)w->data;
+            for (size_t i = 0; i < conv.size(); ++i) conv[i] = host_f32_to_f16(f[i]);
         }
         else
         {
@@ -281,11 +270,11 @@ struct ProfScope
     }
 };
 
-template <int BN, int EPI, int CG, int BFMT>
+template <int BN, int EPI, int CG>
 int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
     using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG>;
-    auto kern = gemm_tcgen05_kernel<BN, EPI, BFMT, CG>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, 0, CG>;
     static bool attr_set = false;
     if (!attr_set)
     {
@@ -312,15 +301,11 @@ int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &
 }
 
 // tmB: box rows = bn / cg.  tmX: f32 [M][ldo] map of the residual/output (EPI_BIAS_RESID_F32 only; ignored otherwise)
-int launch_gemm(vitb200_engine *e, int cg, int bfmt, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
+int launch_gemm(vitb200_engine *e, int cg, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
 #define VB_CASE(BN, EPI)                                                                                         \
     if (bn == BN && epi == EPI)                                                                                  \
-    {                                                                                                            \
-        if (bfmt == 1)                                                                                           \
-            return cg == 2 ? launch_gemm_t<BN, EPI, 2, 1>(e, tmA, tmB, tmX, p, s, num_sms) : launch_gemm_t<BN, EPI, 1, 1>(e, tmA, tmB, tmX, p, s, num_sms); \
-        return cg == 2 ? launch_gemm_t<BN, EPI, 2, 0>(e, tmA, tmB, tmX, p, s, num_sms) : launch_gemm_t<BN, EPI, 1, 0>(e, tmA, tmB, tmX, p, s, num_sms);     \
-    }
+        return cg == 2 ? launch_gemm_t<BN, EPI, 2>(e, tmA, tmB, tmX, p, s, num_sms) : launch_gemm_t<BN, EPI, 1>(e, tmA, tmB, tmX, p, s, num_sms);
     VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
     VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
     VB_CASE(256, EPI_BIAS_RESID_F32) VB_CASE(128, EPI_BIAS_RESID_F32)
@@ -454,7 +439,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         p.M = B * e->NP; p.N = D; p.K = e->KPp; p.bias = e->patch.b; p.out = e->X; p.ldo = D;
         p.pos = e->pos; p.np = e->NP; p.ntok = N;
         ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
-        if (launch_gemm(e, e->cta_group, e->patch.bfmt, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
 
@@ -471,7 +456,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.ldo = 3 * D;
             ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.qkv.bfmt, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
+            if (launch_gemm(e, e->cta_group, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
         }
         if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s)) return 1;
         {
@@ -483,7 +468,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = D; p.K = D; p.bias = L.proj.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_PROJ, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.proj.bfmt, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
+            if (launch_gemm(e, e->cta_group, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
         }
         if (tap && tap_f32(taps->x1, e->X, (size_t)T * D, s)) return 1;
         {
@@ -495,14 +480,14 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D;
             ProfScope ps(e, PK_FC1, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.fc1.bfmt, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
+            if (launch_gemm(e, e->cta_group, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
         }
         if (tap && tap_f16(taps->h, e->H16, (size_t)T * 4 * D, s)) return 1;
         {
             GemmParams p{};
             p.M = T; p.N = D; p.K = 4 * D; p.bias = L.fc2.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_FC2, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.fc2.bfmt, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
+            if (launch_gemm(e, e->cta_group, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
         }
         if (tap && tap_f32(taps->x2, e->X, (size_t)T * D, s)) return 1;
     }
@@ -516,7 +501,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         GemmParams p{};
         p.M = B; p.N = C; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = C;
         ProfScope ps(e, PK_HEAD, 2.0 * p.M * p.N * p.K, s);
-        if (launch_gemm(e, e->cta_group, e->head.bfmt, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, e->tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (d_probs || (k > 0 && (d_topk_idx || d_topk_val)))
     {
@@ -833,8 +818,6 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
 {
     if (!A || !W || !bias || !out) return fail("null argument");
     if (K % 8 != 0) return fail("K must be a multiple of 8");
-    const int bfmt = (epilogue & 0x100) ? 1 : 0; // W holds bf16 bit patterns
-    epilogue &= 0xFF;
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -870,7 +853,7 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
         }
         GemmParams p{};
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.ldo = N; p.resid = (const float *)dO;
-        if (launch_gemm(nullptr, cg, bfmt, bn, epilogue, tA, tB, tX, p, 0, prop.multiProcessorCount)) break;
+        if (launch_gemm(nullptr, cg, bn, epilogue, tA, tB, tX, p, 0, prop.multiProcessorCount)) break;
         cudaError_t err = cudaDeviceSynchronize();
         if (err != cudaSuccess) { fail("GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
         if (f16out)
