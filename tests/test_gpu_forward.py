@@ -206,3 +206,30 @@ def test_f32_model_file_loads_and_matches_within_f16_weight_rounding():
 def test_smoke_entry_point():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.skipif(not (os.path.exists(ref.VIT_REF_BIN) and os.path.exists(os.path.join(os.path.dirname(ref.VIT_REF_BIN), "vit_b200_cli"))),
+                    reason="reference CLI binaries (oracle/_ref) not shipped")
+def test_reference_cli_runs_unmodified_on_the_b200_engine(tmp_path):
+    """Drop-in check at the CLI level: the reference's own main.cpp + loader + stb_image + bicubic preprocess, linked against
+    integration/vit_predict_b200.cpp + libvitb200.so (oracle/_ref/vit_b200_cli), must print the same top-5 lines as the stock
+    reference binary (oracle/_ref/vit_ref) for the same model file and image."""
+    import subprocess
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, size=(300, 280, 3), dtype=np.uint8)
+    ppm = tmp_path / "img.ppm"
+    with open(ppm, "wb") as f:
+        f.write(b"P6\n280 300\n255\n" + img.tobytes())
+    model = model_path("tiny", "f16")
+
+    def top_lines(binary):
+        r = subprocess.run([binary, "-m", model, "-i", str(ppm), "-k", "5", "-t", "4"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [l.strip() for l in r.stdout.splitlines() if l.startswith(" > ")]
+
+    want = top_lines(ref.VIT_REF_BIN)
+    got = top_lines(os.path.join(os.path.dirname(ref.VIT_REF_BIN), "vit_b200_cli"))
+    assert len(want) == 5 and len(got) == 5
+    assert [l.split(":")[0] for l in got] == [l.split(":")[0] for l in want]          # same labels, same order
+    for g, w in zip(got, want):
+        assert abs(float(g.split(":")[1]) - float(w.split(":")[1])) <= 0.011           # printed with %.2f
