@@ -117,8 +117,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     else if (warp_idx == 1)
     {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0)
+        // ===================== MMA issuer: the warp runs the loop uniformly, one elected lane issues =====================
         {
             const uint32_t idesc_s = ptx::umma_idesc_f16(128, p.NKP, 0, 0, 0, 0);
             const uint32_t idesc_o = ptx::umma_idesc_f16(128, 64, 0, 0, 0, /*B (V) is MN-major*/ 1);
@@ -127,10 +126,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             auto issue_s = [&](int st, int t) {
                 const uint64_t kdesc = ptx::umma_desc_kmajor_sw128(sK(st));
                 const uint64_t qdesc = ptx::umma_desc_kmajor_sw128(sQ(st, t));
+                if (ptx::elect_one())
+                {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::tcgen05_mma_f16(tmem_base + scol[t], qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0);
-                ptx::tcgen05_commit(s_full(t));
+                    for (int k = 0; k < 4; ++k)
+                        ptx::tcgen05_mma_f16(tmem_base + scol[t], qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0);
+                    ptx::tcgen05_commit(s_full(t));
+                }
+                __syncwarp();
             };
             int i = 0;
             const int first = blockIdx.x;
@@ -152,10 +155,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (t == 0) { if (i > 0) ptx::mbar_wait(o_empty(p.n_mtiles - 1), (i - 1) & 1); }
                     else ptx::mbar_wait(o_empty(0), i & 1);
                     ptx::tcgen05_fence_after();
-                    for (int j = 0; j < ksteps; ++j) // 16 keys per step: 8 TMEM columns of packed f16, 16 rows (2048 B) of V
-                        ptx::tcgen05_mma_f16_ts(tmem_base + ATT_TC_OCOL, tmem_base + scol[t] + 8 * j, vdesc + (uint64_t)(j * 128), idesc_o, j > 0);
-                    ptx::tcgen05_commit(o_full(t));
-                    if (t == p.n_mtiles - 1) ptx::tcgen05_commit(load_empty(st)); // all MMAs reading this smem stage have retired
+                    if (ptx::elect_one())
+                    {
+                        for (int j = 0; j < ksteps; ++j) // 16 keys per step: 8 TMEM columns of packed f16, 16 rows (2048 B) of V
+                            ptx::tcgen05_mma_f16_ts(tmem_base + ATT_TC_OCOL, tmem_base + scol[t] + 8 * j, vdesc + (uint64_t)(j * 128), idesc_o, j > 0);
+                        ptx::tcgen05_commit(o_full(t));
+                        if (t == p.n_mtiles - 1) ptx::tcgen05_commit(load_empty(st)); // all MMAs reading this smem stage have retired
+                    }
+                    __syncwarp();
                     // S_t of the NEXT problem (other smem stage) goes into the pipe right behind P_t V: the in-order tensor
                     // pipe runs it after P_t V has consumed the aliased P_t columns, so tile t's warpgroup finds its next
                     // scores ready as soon as it has drained O

@@ -273,7 +273,7 @@ struct ProfScope
 template <int BN, int EPI, int CG>
 int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
-    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG>;
+    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32>;
     auto kern = gemm_tcgen05_kernel<BN, EPI, 0, CG>;
     static bool attr_set = false;
     if (!attr_set)
@@ -306,6 +306,12 @@ int launch_gemm(vitb200_engine *e, int cg, int bn, int epi, const CUtensorMap &t
 #define VB_CASE(BN, EPI)                                                                                         \
     if (bn == BN && epi == EPI)                                                                                  \
         return cg == 2 ? launch_gemm_t<BN, EPI, 2>(e, tmA, tmB, tmX, p, s, num_sms) : launch_gemm_t<BN, EPI, 1>(e, tmA, tmB, tmX, p, s, num_sms);
+    if (epi == EPI_PATCH_GATHER_F32) // CTA pairs only (the A producers fill three pipeline stages at a time)
+    {
+        if (cg != 2) return fail("gathered patch embedding needs cta_group 2");
+        return bn == 256 ? launch_gemm_t<256, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, p, s, num_sms)
+                         : launch_gemm_t<128, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, p, s, num_sms);
+    }
     VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
     VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
     VB_CASE(256, EPI_BIAS_RESID_F32) VB_CASE(128, EPI_BIAS_RESID_F32)
@@ -426,8 +432,11 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     e->launches = 0;
     __half *PA = e->PA;
 
-    // patch embedding: im2col-free gather + GEMM with conv bias + pos_embed epilogue (vit.cpp:772-797)
-    if (launch_patchify(e, d_images, PA, B, s)) return 1;
+    // patch embedding (vit.cpp:772-797).  P = 16 with CTA pairs: ONE kernel -- the GEMM's A producers gather the f32 pixels
+    // straight into the tcgen05 operand tiles (no im2col buffer) and the epilogue adds conv bias + pos_embed and writes token
+    // rows.  Other patch sizes: patchify_f16_kernel materialises the f16 patch matrix first.
+    const bool fused_patch = e->hp.patch_size == 16 && e->cta_group == 2;
+    if (!fused_patch && launch_patchify(e, d_images, PA, B, s)) return 1;
     {
         const int n = B * D, threads = 256;
         cls_rows_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(e->X, e->cls, e->pos, B, N, D);
@@ -438,8 +447,9 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         GemmParams p{};
         p.M = B * e->NP; p.N = D; p.K = e->KPp; p.bias = e->patch.b; p.out = e->X; p.ldo = D;
         p.pos = e->pos; p.np = e->NP; p.ntok = N;
+        p.img = d_images; p.S = e->hp.img_size; p.G = e->G;
         ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
-        if (launch_gemm(e, e->cta_group, e->patch.bn, EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->patch.bn, fused_patch ? EPI_PATCH_GATHER_F32 : EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
 

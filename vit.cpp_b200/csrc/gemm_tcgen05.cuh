@@ -25,6 +25,7 @@ enum GemmEpilogue
     EPI_BIAS_RESID_F32 = 2, // out f32 = (acc + bias) + resid                         (proj, fc2; vit.cpp:873,900)
     EPI_PATCH_F32 = 3,      // out f32[token row] = (acc + bias) + pos_embed           (patch embed; vit.cpp:773-797)
     EPI_BIAS_F32 = 4,       // out f32 = acc + bias                                   (head logits)
+    EPI_PATCH_GATHER_F32 = 5, // EPI_PATCH_F32 with the A operand gathered straight from the f32 HWC pixels (P = 16): no im2col buffer
 };
 
 struct GemmParams
@@ -36,6 +37,8 @@ struct GemmParams
     const float *resid; // EPI_BIAS_RESID_F32: [M][ldo] (may alias out)
     const float *pos;   // EPI_PATCH_F32: pos_embed [ntok][N]
     int np, ntok;       // EPI_PATCH_F32: patches / tokens per image
+    const float *img;   // EPI_PATCH_GATHER_F32: images [B][S][S][3] f32 (image_f32 layout, vit.h:98-103)
+    int S, G;           // EPI_PATCH_GATHER_F32: image side, patches per side
 };
 
 constexpr int GEMM_BM = 128;
@@ -47,14 +50,16 @@ constexpr int GEMM_BK = 64;
 // CG = CTAs per MMA (cta_group): 2 = a CTA pair on one TPC computes a 256 x BN tile with M = 256 tcgen05.mma; each CTA
 // stages its own 128 A rows and HALF of the W tile (the pair shares both halves), which halves the per-SM shared-memory
 // traffic of the B operand -- the 1-CTA kernel is shared-memory-bandwidth bound at ~70 % tensor-pipe utilisation.
-template <int BN, bool kResid, int CG>
+template <int BN, bool kResid, int CG, bool kGather = false>
 struct GemmCfg
 {
     static constexpr int kResidRing = 5;
     // epilogue warps: 4 for the TMA-ring residual epilogue (HBM-bound), 8 otherwise (two per TMEM lane quarter, splitting
     // the columns) so the ALU-heavy f16 epilogues (bias, GELU, packing) have two warps per SM sub-partition to overlap
     static constexpr int kEpiWarps = kResid ? 4 : 8;
-    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kGatherWarps = kGather ? 4 : 0; // patch-embedding A producers (thread = one patch row of the tile)
+    static constexpr int kFirstEpiWarp = 2 + kGatherWarps;
+    static constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_ROWS = BN / CG;               // W rows staged by this CTA
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
@@ -62,7 +67,8 @@ struct GemmCfg
     static constexpr int BAR_BYTES = 512;
     static constexpr int kSmemLimit = 232448; // 227 KB per CTA
     static constexpr int kStagesFit = (kSmemLimit - 1024 - STAGE_BYTES - BAR_BYTES) / (A_BYTES + B_BYTES);
-    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit; // operand ring depth: whatever fits
+    static constexpr int kStagesFit8 = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr int kStages = kGather ? kStagesFit8 / 3 * 3 : kStagesFit8; // operand ring depth: whatever fits (gather fills 3 at a time)
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * (A_BYTES + B_BYTES) + STAGE_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -81,12 +87,15 @@ __device__ __forceinline__ float gelu_tanh_f32(float x)
 }
 
 template <int BN, int EPI, int B_FMT, int CG>
-__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG>::kThreads), 1)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32>::kThreads), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const GemmParams p)
 {
     constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32);
-    using Cfg = GemmCfg<BN, kResid, CG>;
+    constexpr bool kGather = (EPI == EPI_PATCH_GATHER_F32);
+    constexpr bool kPatch = (EPI == EPI_PATCH_F32 || EPI == EPI_PATCH_GATHER_F32);
+    using Cfg = GemmCfg<BN, kResid, CG, kGather>;
+    static_assert(!kGather || (CG == 2 && Cfg::kStages % 3 == 0 && Cfg::kStages >= 3), "gathered patch embedding: CTA pairs, stages in threes");
     constexpr int TILE_M = GEMM_BM * CG; // rows of C per CTA group
     constexpr int kStages = Cfg::kStages;
     constexpr bool kOutF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
@@ -129,7 +138,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
         for (int s = 0; s < kStages; ++s)
         {
-            ptx::mbar_init(full_bar(s), CG); // one (remote) arrival per producer of the pair; leader's barrier collects all bytes
+            // one (remote) arrival per producer of the pair (+ one per gather warp); the leader's barrier collects all bytes
+            ptx::mbar_init(full_bar(s), CG * (1 + Cfg::kGatherWarps));
             ptx::mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a)
@@ -142,7 +152,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int r = 0; r < Cfg::kResidRing; ++r) ptx::mbar_init(rfull_bar(w, r), 1);
         ptx::fence_barrier_init();
     }
-    if (warp_idx == 2)
+    if (warp_idx == Cfg::kFirstEpiWarp)
     {
         if constexpr (CG == 2) { ptx::tcgen05_alloc_cg2(tmem_ptr_addr, Cfg::TMEM_COLS); ptx::tcgen05_relinquish_cg2(); }
         else { ptx::tcgen05_alloc(tmem_ptr_addr, Cfg::TMEM_COLS); ptx::tcgen05_relinquish(); }
@@ -167,7 +177,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = 0; kb < num_kb; ++kb)
                 {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1); // own slot free (the MMA commit is multicast to both CTAs)
-                    if constexpr (CG == 2)
+                    if constexpr (kGather)
+                    {
+                        // W only; k-blocks visited as (ky group, channel): k = c*256 + kyg*64 (K order c*P*P + ky*P + kx, ggml.c:11597)
+                        const int koff = (kb % 3) * 256 + (kb / 3) * 64;
+                        if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::B_BYTES);
+                        else ptx::mbar_arrive_remote(full_bar(stage), 0);
+                        ptx::tma_load_2d_cg2(sB + stage * Cfg::B_BYTES, &tmB, full_bar(stage), koff, b_row);
+                    }
+                    else if constexpr (CG == 2)
                     {
                         // all bytes of the pair are accounted on the LEADER's full barrier
                         if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
@@ -189,8 +207,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     else if (warp_idx == 1)
     {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0 && cta_rank == 0) // the leader CTA issues for the whole group
+        // ===================== MMA issuer: whole warp runs the loop (uniform), one elected lane issues =====================
+        if (cta_rank == 0) // the leader CTA issues for the whole group
         {
             constexpr uint32_t idesc = ptx::umma_idesc_f16(TILE_M, BN, /*a=f16*/ 0, B_FMT);
             int stage = 0;
@@ -209,28 +227,104 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     ptx::tcgen05_fence_after();
                     const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sA + stage * Cfg::A_BYTES);
                     const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sB + stage * Cfg::B_BYTES);
+                    if (ptx::elect_one())
+                    {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                    {
-                        // advance 16 f16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-                        if constexpr (CG == 2) ptx::tcgen05_mma_f16_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                        else ptx::tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < GEMM_BK / 16; ++k)
+                        {
+                            // advance 16 f16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+                            if constexpr (CG == 2) ptx::tcgen05_mma_f16_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            else ptx::tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if constexpr (CG == 2)
+                        {
+                            ptx::tcgen05_commit_cg2(empty_bar(stage), 3); // frees the slot in BOTH CTAs when these MMAs retire
+                            if (kb == num_kb - 1) ptx::tcgen05_commit_cg2(tfull_bar(as), 3); // accumulator complete, both epilogues
+                        }
+                        else
+                        {
+                            ptx::tcgen05_commit(empty_bar(stage)); // frees the smem slot when these MMAs retire
+                            if (kb == num_kb - 1) ptx::tcgen05_commit(tfull_bar(as)); // accumulator complete
+                        }
                     }
-                    if constexpr (CG == 2)
-                    {
-                        ptx::tcgen05_commit_cg2(empty_bar(stage), 3); // frees the slot in BOTH CTAs when these MMAs retire
-                        if (kb == num_kb - 1) ptx::tcgen05_commit_cg2(tfull_bar(as), 3); // accumulator complete, both epilogues
-                    }
-                    else
-                    {
-                        ptx::tcgen05_commit(empty_bar(stage)); // frees the smem slot when these MMAs retire
-                        if (kb == num_kb - 1) ptx::tcgen05_commit(tfull_bar(as)); // accumulator complete
-                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
+    }
+    else if (kGather && warp_idx < Cfg::kFirstEpiWarp)
+    {
+        // ===================== A producers: im2col-free gather (patch size 16) =====================
+        // Replaces ggml_im2col (ggml.c:11528-11608) + the HWC->CHW copy (vit.cpp:759-768): stride == kernel makes im2col a pure
+        // permutation, so each thread owns one patch (one A row): per group of 4 kernel rows it reads the 4 x 16 pixels x 3
+        // channels (4 x 192 contiguous bytes, 128-bit loads), rounds to f16 (RNE, ggml.c:11599) and writes the three channels'
+        // 64-wide K slices into three consecutive pipeline stages in the UMMA SWIZZLE_128B layout.
+        if constexpr (kGather)
+        {
+            const int r = (warp_idx - 2) * 32 + lane; // row of this CTA's 128 x 64 A tile
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = group_id; tile < num_tiles; tile += num_groups)
+            {
+                const int m_blk = tile / n_tiles;
+                const int m = m_blk * TILE_M + (int)cta_rank * GEMM_BM + r; // patch index (row of the virtual im2col matrix)
+                const bool valid = m < p.M;
+                const int img_i = valid ? m / p.np : 0, pp = valid ? m - img_i * p.np : 0;
+                const int py = pp / p.G, px = pp - py * p.G;
+                const float *patch0 = p.img + (((size_t)img_i * p.S + (size_t)py * 16) * p.S + (size_t)px * 16) * 3;
+                for (int kg = 0; kg < num_kb / 3; ++kg) // kernel rows 4*kg .. 4*kg+3
+                {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) ptx::mbar_wait(empty_bar(stage + u), phase ^ 1);
+#pragma unroll
+                    for (int ky = 0; ky < 4; ++ky)
+                    {
+                        float v[48];
+                        const float4 *src = reinterpret_cast<const float4 *>(patch0 + (size_t)(kg * 4 + ky) * p.S * 3);
+#pragma unroll
+                        for (int i = 0; i < 12; ++i)
+                        {
+                            const float4 f = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                        {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) // pixels 0..7 / 8..15 of the kernel row -> one 16-byte chunk each
+                            {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                {
+                                    const __half2 h2 = __floats2half2_rn(v[(hh * 8 + 2 * e) * 3 + c], v[(hh * 8 + 2 * e + 1) * 3 + c]);
+                                    w[e] = *reinterpret_cast<const uint32_t *>(&h2);
+                                }
+                                const int chunk = ky * 2 + hh; // 16-B chunk inside the 128-B K slice of this row
+                                uint4 *dst = reinterpret_cast<uint4 *>(smem + (size_t)(stage + c) * Cfg::A_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                *dst = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        }
+                    }
+                    ptx::fence_proxy_async_smem(); // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+#pragma unroll
+                        for (int u = 0; u < 3; ++u)
+                        {
+                            if (cta_rank == 0) ptx::mbar_arrive(full_bar(stage + u));
+                            else ptx::mbar_arrive_remote_release(full_bar(stage + u), 0);
+                        }
+                    }
+                    __syncwarp();
+                    stage += 3;
+                    if (stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
     }
     else
     {
@@ -246,7 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // place and lane 0 TMA-stores the slot.  In-place on X is safe: a chunk is stored only after its own load
             // completed, and prefetched chunks belong to other tiles / columns.
             constexpr int R = Cfg::kResidRing;
-            const int ew = warp_idx - 2;
+            const int ew = warp_idx - Cfg::kFirstEpiWarp;
             uint8_t *ring = stg_base + ew * (R * 4096);
             const uint32_t ring_u32 = ptx::smem_u32(ring);
             auto n_chunks_of = [&](int tile) { const int n0 = (tile % n_tiles) * BN; const int rem = p.N - n0; return (rem >= BN ? BN : rem + 31) / 32; };
@@ -322,8 +416,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         else
         {
-        uint8_t *stg = stg_base + (warp_idx - 2) * 4096;
-        const int half_sel = (warp_idx - 2) >> 2; // warps w and w+4 share a TMEM lane quarter and alternate column passes
+        uint8_t *stg = stg_base + (warp_idx - Cfg::kFirstEpiWarp) * 4096;
+        const int half_sel = (warp_idx - Cfg::kFirstEpiWarp) >> 2; // warps w and w+4 share a TMEM lane quarter and alternate column passes
         for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it)
         {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -439,7 +533,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const float4 r = *reinterpret_cast<const float4 *>(p.resid + (size_t)grow * p.ldo + gcol);
                                 a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
                             }
-                            if constexpr (EPI == EPI_PATCH_F32)
+                            if constexpr (kPatch)
                             {
                                 const int img = grow / p.np, pp = grow - img * p.np;
                                 orow = (size_t)img * p.ntok + 1 + pp;
@@ -459,7 +553,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== teardown =====================
     ptx::tcgen05_fence_before();
     if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads(); // the peer may still be reading its TMEM / signalling our barriers
-    if (warp_idx == 2)
+    if (warp_idx == Cfg::kFirstEpiWarp)
     {
         ptx::tcgen05_fence_after();
         if constexpr (CG == 2) ptx::tcgen05_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);

@@ -17,6 +17,21 @@ __device__ __forceinline__ uint32_t lane_id()
     return l;
 }
 
+// One lane of a converged warp (the same lane every time).  Used instead of `if (lane == 0)` around tcgen05 / TMA issue:
+// the surrounding code then stays warp-uniform, so descriptors live in uniform registers and each UTCHMMA costs one
+// instruction instead of an ELECT / R2UR / BRA.U.ANY loop per operand (ncu: the single-thread form issued ~105 SASS
+// instructions per k-block and capped the tensor pipe at ~73 %).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -76,6 +91,19 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta)
         "{\n\t.reg .b32 r;\n\t"
         "mapa.shared::cluster.u32 r, %0, %1;\n\t"
         "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
+
+// Same with release semantics at cluster scope: orders this thread's prior shared-memory writes (made visible to the async
+// proxy by fence.proxy.async) before the arrival is observed in the other CTA.  Costs a GPU-scope MEMBAR: use only off the
+// hot loop (the gathered patch-embedding producer).
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 r;\n\t"
+        "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}"
         ::"r"(bar), "r"(cta)
         : "memory");
 }
