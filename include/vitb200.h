@@ -83,6 +83,15 @@ int vitb200_forward_async(vitb200_engine *e, const float *images, int batch, flo
                           int32_t *topk_idx, float *topk_prob, int k);
 int vitb200_sync(vitb200_engine *e);
 
+/* vit_image_preprocess + vit_predict fused on the GPU (reference vit.h:119, vit.cpp:130-305 + vit.cpp:1004): `images[b]` is the
+ * interleaved RGB u8 image the reference's load_image_from_file produces (image_u8::data, vit.h:91-96), nx[b] x ny[b]
+ * pixels, any size.  bilinear = 0 selects the reference's default bicubic path (hparams.interpolation, vit.h:30).  The resize,
+ * the round-to-u8 and the mean/std normalisation run on the device and feed the forward pass directly; images_f32_out
+ * (optional, host, [batch][img][img][3]) returns the pre-processed image_f32 batch.  probs/logits/top-k as vitb200_forward;
+ * all of them NULL = preprocess only. */
+int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
+                       float *images_f32_out, float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k);
+
 /* Same with DEVICE buffers on the engine's device, enqueued on `stream` (a cudaStream_t; NULL = the engine's own
  * stream) without synchronising: the caller owns ordering.  This is the resident-data path bench.py times. */
 int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, float *d_probs, float *d_logits,

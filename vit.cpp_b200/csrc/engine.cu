@@ -6,6 +6,7 @@
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "attention_tcgen05.cuh"
+#include "preprocess.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -140,6 +141,10 @@ struct vitb200_engine
     int32_t *d_topk_idx_slot[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     unsigned long long submits = 0;
+    // GPU preprocessing (vitb200_forward_u8): u8 staging buffer + per-image descriptors, grown on demand
+    uint8_t *d_u8 = nullptr;
+    size_t d_u8_cap = 0;
+    PreImage *d_pre = nullptr;
     // CUDA-graph cache for the kernel schedule of one forward, keyed by its arguments (launch-bound inner loop: ~90 kernels)
     struct GraphEntry { const void *img; int batch; void *probs, *logits, *tidx, *tval; int k; int state; int launches; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;
@@ -690,6 +695,8 @@ void vitb200_destroy(vitb200_engine *e)
     cudaSetDevice(e->device);
     for (void *p : e->allocs) cudaFree(p);
     for (auto &g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (e->d_u8) cudaFree(e->d_u8);
+    if (e->d_pre) cudaFree(e->d_pre);
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -821,6 +828,60 @@ int vitb200_forward(vitb200_engine *e, const float *images, int batch, float *pr
 int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, const vitb200_taps *taps)
 {
     return forward_host(e, images, batch, probs, logits, nullptr, nullptr, 0, taps);
+}
+
+// vit_image_preprocess (reference vit.cpp:289-305) for a batch of u8 RGB images of arbitrary sizes, on the GPU, followed by the
+// forward pass: the "images" of vitb200_forward never exist on the host.  images_f32_out (optional, HOST) receives the
+// pre-processed image_f32 batch for inspection.
+int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
+                       float *images_f32_out, float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k)
+{
+    if (!e || !images || !nx || !ny) return fail("null argument");
+    if (batch < 1 || batch > e->max_batch) return fail("batch %d out of range (1..%d)", batch, e->max_batch);
+    if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(vitb200_sync(e) == 0 ? cudaSuccess : cudaErrorUnknown); // the staging buffer is not double-buffered
+    std::vector<PreImage> pre((size_t)batch);
+    size_t total = 0;
+    for (int b = 0; b < batch; ++b)
+    {
+        if (!images[b] || nx[b] < 1 || ny[b] < 1) return fail("image %d: bad pointer or size", b);
+        pre[b].offset = total; pre[b].nx = nx[b]; pre[b].ny = ny[b];
+        total += ((size_t)nx[b] * ny[b] * 3 + 255) / 256 * 256;
+    }
+    if (total > e->d_u8_cap)
+    {
+        if (e->d_u8) cudaFree(e->d_u8);
+        e->d_u8 = nullptr; e->d_u8_cap = 0;
+        CUDA_TRY(cudaMalloc((void **)&e->d_u8, total));
+        e->d_u8_cap = total;
+    }
+    if (!e->d_pre) CUDA_TRY(cudaMalloc((void **)&e->d_pre, (size_t)e->max_batch * sizeof(PreImage)));
+    cudaStream_t s = e->stream;
+    for (int b = 0; b < batch; ++b)
+        CUDA_TRY(cudaMemcpyAsync(e->d_u8 + pre[b].offset, images[b], (size_t)nx[b] * ny[b] * 3, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pre, pre.data(), (size_t)batch * sizeof(PreImage), cudaMemcpyHostToDevice, s));
+    const int S = e->hp.img_size;
+    dim3 grid((unsigned)((S * S + 255) / 256), (unsigned)batch);
+    preprocess_kernel<<<grid, 256, 0, s>>>(e->d_u8, e->d_pre, e->d_img, S, bilinear ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    const size_t img_elems = (size_t)3 * S * S;
+    if (images_f32_out) CUDA_TRY(cudaMemcpyAsync(images_f32_out, e->d_img, (size_t)batch * img_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    const bool want_topk = k > 0 && (topk_idx || topk_prob);
+    const int C = e->hp.num_classes;
+    if (probs || logits || want_topk)
+    {
+        if (run_forward_graphed(e, e->d_img, batch, (probs || want_topk) ? e->d_probs : nullptr, e->d_logits, want_topk ? e->d_topk_idx : nullptr,
+                                want_topk ? e->d_topk_val : nullptr, want_topk ? k : 0, s))
+            return 1;
+        e->launches += 1;
+        if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx, (size_t)batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val, (size_t)batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
 }
 
 int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W, const float *bias,

@@ -64,6 +64,7 @@ def lib():
         L.vitb200_sync.argtypes = [vp]
         L.vitb200_profile_enable.argtypes = [vp, i32]
         L.vitb200_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.vitb200_forward_u8.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32]
         L.vitb200_forward_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp]
         L.vitb200_last_launch_count.argtypes = [vp]
         L.vitb200_stream.argtypes = [vp]
@@ -138,6 +139,27 @@ def vit_predict(model: VitModel, images: np.ndarray, topk: int = 5, want_logits:
                                  logits.ctypes.data if want_logits else None, idx.ctypes.data, val.ctypes.data, topk),
            "vit_predict")
     return (probs, idx, val, logits) if want_logits else (probs, idx, val)
+
+
+def vit_image_preprocess_predict(model: VitModel, images_u8, bilinear: bool = False, topk: int = 5, predict: bool = True):
+    """reference vit_image_preprocess (vit.cpp:289) + vit_predict on the GPU for a list of HxWx3 uint8 RGB arrays of any size.
+    Returns (image_f32 batch [B,S,S,3], probs, topk_idx, topk_prob, logits); the last four are None if predict is False."""
+    imgs = [np.ascontiguousarray(a, dtype=np.uint8) for a in images_u8]
+    B = len(imgs)
+    ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in imgs])
+    nx = (C.c_int * B)(*[a.shape[1] for a in imgs])
+    ny = (C.c_int * B)(*[a.shape[0] for a in imgs])
+    S = model.img_size
+    f32 = np.empty((B, S, S, 3), np.float32)
+    probs = np.empty((B, model.num_classes), np.float32) if predict else None
+    logits = np.empty((B, model.num_classes), np.float32) if predict else None
+    idx = np.empty((B, topk), np.int32) if predict else None
+    val = np.empty((B, topk), np.float32) if predict else None
+    _check(lib().vitb200_forward_u8(model.handle, ptrs, nx, ny, B, int(bilinear), f32.ctypes.data,
+                                    probs.ctypes.data if predict else None, logits.ctypes.data if predict else None,
+                                    idx.ctypes.data if predict else None, val.ctypes.data if predict else None, topk if predict else 0),
+           "vit_image_preprocess")
+    return f32, probs, idx, val, logits
 
 
 TAP_SHAPES = {
