@@ -83,6 +83,12 @@ int vitb200_forward_async(vitb200_engine *e, const float *images, int batch, flo
                           int32_t *topk_idx, float *topk_prob, int k);
 int vitb200_sync(vitb200_engine *e);
 
+/* Data-parallel vitb200_forward over n_engines engines (one per GPU of the box, same model, weights replicated) from one host
+ * thread: contiguous image shards, no collective (images are independent units).  batch may exceed one engine's max_batch
+ * as long as every shard fits. */
+int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs, float *logits,
+                            int32_t *topk_idx, float *topk_prob, int k);
+
 /* vit_image_preprocess + vit_predict fused on the GPU (reference vit.h:119, vit.cpp:130-305 + vit.cpp:1004): `images[b]` is the
  * interleaved RGB u8 image the reference's load_image_from_file produces (image_u8::data, vit.h:91-96), nx[b] x ny[b]
  * pixels, any size.  bilinear = 0 selects the reference's default bicubic path (hparams.interpolation, vit.h:30).  The resize,

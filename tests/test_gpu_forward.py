@@ -277,3 +277,22 @@ def test_forward_u8_end_to_end_vs_reference_pipeline():
         assert idx[b, 0] == l_ref.argmax()
     m.close()
     rm.close()
+
+
+def test_in_process_sharding_over_all_visible_gpus():
+    """SURVEY.md 8e process model: one host thread, one engine per GPU, contiguous image shards, no collective.  With a single
+    visible GPU this still exercises the sharding arithmetic (two engines on device 0)."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    devs = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    path = model_path("tiny", "f16")
+    models = [eng.vit_model_load(path, d, 4) for d in devs]
+    imgs = gf.synthetic_images(7, models[0].img_size, seed=6)  # ragged: 7 images over the engines
+    probs, idx, val = eng.vit_predict_sharded(models, imgs, 5)
+    p1, i1, v1 = eng.vit_predict(models[0], imgs[:4], 5)
+    assert np.array_equal(probs[:4], p1) and np.array_equal(idx[:4], i1)
+    p2, i2, v2 = eng.vit_predict(models[-1], imgs[4:], 5)
+    assert np.array_equal(idx[4:], i2)
+    np.testing.assert_allclose(probs[4:], p2, rtol=0, atol=1e-6)
+    for m in models:
+        m.close()

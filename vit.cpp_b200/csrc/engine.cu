@@ -280,11 +280,14 @@ int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &
 {
     using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32>;
     auto kern = gemm_tcgen05_kernel<BN, EPI, 0, CG>;
-    static bool attr_set = false;
-    if (!attr_set)
+    // the opt-in to > 48 KB dynamic shared memory is per device (one engine per device, possibly several per process)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63])
     {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     const int m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG), n_tiles = (p.N + BN - 1) / BN;
     const int tiles = m_tiles * n_tiles;
@@ -365,11 +368,13 @@ int launch_attention_t(vitb200_engine *e, int B, cudaStream_t s)
     const int Npad = (N + ATT_KC - 1) / ATT_KC * ATT_KC;
     const int smem = 2 * Npad * 128;
     auto kern = attention_kernel<NW>;
-    static int smem_set = 0;
-    if (smem > smem_set)
+    static int smem_set[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (smem > smem_set[dev & 63])
     {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
+        smem_set[dev & 63] = smem;
     }
     kern<<<B * H, NW * 32, smem, s>>>(e->QKV16, e->A16, N, D, H, Npad, 1.0f / sqrtf((float)(D / H)));
     CUDA_TRY(cudaGetLastError());
@@ -387,11 +392,13 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
     p.kv_bytes = (p.NKP * 128 + 1023) / 1024 * 1024;
     p.scale = 1.0f / sqrtf((float)(p.D / p.H));
     const int smem = 1024 + 2 * (2 * 16384 + 2 * p.kv_bytes) + 256;
-    static int smem_set = 0;
-    if (smem > smem_set)
+    static int smem_set[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (smem > smem_set[dev & 63])
     {
         CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
+        smem_set[dev & 63] = smem;
     }
     const int grid = p.n_problems < e->num_sms ? p.n_problems : e->num_sms;
     attention_tc_kernel<<<grid, ATT_TC_THREADS, smem, s>>>(e->tmQ, e->tmKV, p);
@@ -817,6 +824,37 @@ static int forward_host(vitb200_engine *e, const float *images, int batch, float
 {
     if (forward_enqueue(e, images, batch, probs, logits, topk_idx, topk_prob, k, taps)) return 1;
     return vitb200_sync(e);
+}
+
+// Data-parallel forward over several engines (one per GPU, weights replicated) driven from ONE host thread: image b goes to
+// engine floor(b * n / batch)-style contiguous shards, every shard is enqueued with the non-blocking pipeline entry point, then
+// all engines are synchronised.  No collective: shards are independent.
+int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs, float *logits,
+                            int32_t *topk_idx, float *topk_prob, int k)
+{
+    if (!engines || n_engines < 1 || !images) return fail("null argument");
+    const vitb200_engine *e0 = engines[0];
+    if (!e0) return fail("null engine");
+    const size_t img_elems = (size_t)3 * e0->hp.img_size * e0->hp.img_size;
+    const int C = e0->hp.num_classes;
+    const int base = batch / n_engines, rem = batch % n_engines;
+    int begin = 0;
+    for (int g = 0; g < n_engines; ++g)
+    {
+        const int cnt = base + (g < rem ? 1 : 0);
+        if (cnt == 0) continue;
+        if (!engines[g]) return fail("null engine %d", g);
+        if (engines[g]->hp.img_size != e0->hp.img_size || engines[g]->hp.num_classes != C) return fail("engine %d holds a different model", g);
+        if (vitb200_forward_async(engines[g], images + (size_t)begin * img_elems, cnt, probs ? probs + (size_t)begin * C : nullptr,
+                                  logits ? logits + (size_t)begin * C : nullptr, topk_idx ? topk_idx + (size_t)begin * k : nullptr,
+                                  topk_prob ? topk_prob + (size_t)begin * k : nullptr, k))
+            return 1;
+        begin += cnt;
+    }
+    int rc = 0;
+    for (int g = 0; g < n_engines; ++g)
+        if (engines[g] && vitb200_sync(engines[g])) rc = 1;
+    return rc;
 }
 
 int vitb200_forward(vitb200_engine *e, const float *images, int batch, float *probs, float *logits, int32_t *topk_idx,

@@ -64,6 +64,7 @@ def lib():
         L.vitb200_sync.argtypes = [vp]
         L.vitb200_profile_enable.argtypes = [vp, i32]
         L.vitb200_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.vitb200_forward_sharded.argtypes = [vp, i32, f32p, i32, f32p, f32p, vp, f32p, i32]
         L.vitb200_forward_u8.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32]
         L.vitb200_forward_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp]
         L.vitb200_last_launch_count.argtypes = [vp]
@@ -139,6 +140,20 @@ def vit_predict(model: VitModel, images: np.ndarray, topk: int = 5, want_logits:
                                  logits.ctypes.data if want_logits else None, idx.ctypes.data, val.ctypes.data, topk),
            "vit_predict")
     return (probs, idx, val, logits) if want_logits else (probs, idx, val)
+
+
+def vit_predict_sharded(models, images: np.ndarray, topk: int = 5):
+    """Data-parallel batched vit_predict over several VitModel engines (one per GPU) from one host thread."""
+    imgs = np.ascontiguousarray(images, dtype=np.float32)
+    B = imgs.shape[0]
+    nc = models[0].num_classes
+    probs = np.empty((B, nc), np.float32)
+    idx = np.empty((B, topk), np.int32)
+    val = np.empty((B, topk), np.float32)
+    hs = (C.c_void_p * len(models))(*[m.handle for m in models])
+    _check(lib().vitb200_forward_sharded(hs, len(models), imgs.ctypes.data, B, probs.ctypes.data, None, idx.ctypes.data,
+                                         val.ctypes.data, topk), "vit_predict_sharded")
+    return probs, idx, val
 
 
 def vit_image_preprocess_predict(model: VitModel, images_u8, bilinear: bool = False, topk: int = 5, predict: bool = True):

@@ -35,7 +35,7 @@ CONFIGS = {
     # small shapes for fast unit tests (not reference configs)
     "micro": (128, 2, 2, 16, 64),
     "micro14": (128, 2, 2, 14, 56),
-    # ViT-L/16-384 geometry (hidden 1024, 16 heads, 577 tokens) cut to 2 layers so the CPU oracle stays fast
+    # ViT-L/16-384 geometry (hidden 1024, 16 heads, 577 tokens) cut to 2 layers so CPU-side checks stay fast
     "large384x2": (1024, 2, 16, 16, 384),
 }
 
