@@ -146,6 +146,11 @@ int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, flo
 int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W,
                       const float *bias, const float *resid, float *out);
 
+/* Host-only: the upload-time weight conversion of one quantised tensor, `n_blocks` ggml blocks of 32 weights
+ * (type = ggml_type / file ftype: 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0; ggml-quants.h:11-47) -> f16 bits, exactly what
+ * vitb200_create stores on the device.  Needs no GPU.  Follows dequantize_row_q* (ggml-quants.c:1074-1185). */
+int vitb200_test_dequant(int type, const void *blocks, int64_t n_blocks, uint16_t *out_f16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,8 @@ from oracle import ref  # noqa: E402
 CASES = [  # (config, ftype tag, n_images)
     ("micro", "f16", 4), ("micro14", "f16", 4), ("micro", "f32", 2), ("micro", "q8_0", 2),
     ("tiny", "f16", 4), ("tiny", "q8_0", 2), ("base", "f16", 4), ("base", "q8_0", 2),
+    ("micro", "q4_0", 2), ("micro", "q4_1", 2), ("micro", "q5_0", 2), ("micro", "q5_1", 2),
+    ("tiny", "q4_0", 2), ("tiny", "q5_1", 2), ("base", "q4_1", 2), ("base", "q5_0", 2),
 ]
 
 
@@ -32,7 +34,10 @@ def sha256(path):
 
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])  # optional: regenerate just these "<config>_<ftype>" fixtures
     for cfg, ft, n in CASES:
+        if only and f"{cfg}_{ft}" not in only:
+            continue
         path = model_path(cfg, ft)
         m = ref.RefModel(path)
         imgs = gf.synthetic_images(n, m.img, seed=1234)

@@ -170,13 +170,17 @@ def test_error_paths():
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (reference quantize binary) not shipped")
-@pytest.mark.parametrize("cfg", ["micro", "tiny", "base"])
-def test_q8_0_model_file_top_k_and_noise_floor(cfg):
-    """BASELINE.json configs[4] format: a q8_0 file written by the reference's own quantize.  The reference multiplies int8
-    weights with dynamically quantised int8 activations; no non-bit-identical implementation gets closer than ~1.6e-2 to that
-    (SURVEY.md 7.4), so the binding criteria are identical top-k and an error at that floor, against the q8_0 oracle."""
-    g = np.load(os.path.join(GOLD, f"{cfg}_q8_0.npz"))
-    m = eng.vit_model_load(model_path(cfg, "q8_0"), 0, 4)
+@pytest.mark.parametrize("cfg,fmt", [("micro", "q8_0"), ("tiny", "q8_0"), ("base", "q8_0"),
+                                     ("micro", "q4_0"), ("micro", "q4_1"), ("micro", "q5_0"), ("micro", "q5_1"),
+                                     ("tiny", "q4_0"), ("tiny", "q5_1"), ("base", "q4_1"), ("base", "q5_0")])
+def test_quantised_model_file_top_k_and_noise_floor(cfg, fmt):
+    """BASELINE.json configs[4] format (q8_0) and the other block formats vit_model_load accepts (vit.cpp:645-672: q4_0, q4_1,
+    q5_0, q5_1), files written by the reference's own quantize.  The reference multiplies the integer weights with activations
+    quantised on the fly to int8; no non-bit-identical implementation gets closer than ~1.6e-2 to that (the
+    dequantised-weight x f16-activation recipe measured on the CPU sits at 1.0e-2..2.0e-2 for every format), so the binding
+    criteria are identical top-1, gap-aware top-5 and an error at that floor, against the reference's own output."""
+    g = np.load(os.path.join(GOLD, f"{cfg}_{fmt}.npz"))
+    m = eng.vit_model_load(model_path(cfg, fmt), 0, 4)
     imgs = gf.synthetic_images(int(g["n_images"]), m.img_size, seed=int(g["image_seed"]))
     probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
     re = rel_err(logits, g["logits"])

@@ -122,3 +122,37 @@ def test_synthetic_images_are_preprocess_range():
     x = gf.synthetic_images(2, 32, seed=1)
     assert x.dtype == np.float32 and x.shape == (2, 32, 32, 3)
     assert x.min() >= -2.2 and x.max() <= 2.7
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_block_dequant_matches_ggml(name):
+    """The upload-time weight conversion (C++ in the library, numpy in the file tooling) against ggml's own
+    ggml_quantize_* / dequantize_row_* (ggml-quants.c:1074-1185) compiled from the reference tree: f32 values identical,
+    engine output = their f16 rounding."""
+    import ctypes
+    from tests.util import pkg
+    ft = gf.QUANT_NAMES[name]
+    L = ref.lib()
+    ref.RefModel(model_path("micro", "f16")).close()   # ggml_init fills the f16->f32 table dequantize_row_* reads
+    rng = np.random.default_rng(ft)
+    n = 32 * 257
+    src = (rng.normal(0, 0.05, n) * rng.choice([1.0, 8.0, 0.01], n)).astype(np.float32)
+    bs = gf.QUANT_BLOCK_BYTES[ft]
+    blocks = np.zeros(n // 32 * bs, np.uint8)
+    hist = np.zeros(16, np.int64)
+    quant = getattr(L, f"ggml_quantize_{name}")
+    quant.restype = ctypes.c_size_t
+    quant.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    assert quant(src.ctypes.data, blocks.ctypes.data, n, n, hist.ctypes.data) == blocks.size
+    want = np.empty(n, np.float32)
+    deq = getattr(L, f"dequantize_row_{name}")
+    deq.restype = None
+    deq.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    deq(blocks.ctypes.data, want.ctypes.data, n)
+    got_np = gf.dequant_blocks(ft, blocks, n)
+    assert np.array_equal(got_np, want) or np.abs(got_np - want).max() <= 2.0 ** -24 * np.abs(want).max()  # *_1: fma or not
+    got_eng = pkg.engine.test_dequant(ft, blocks)
+    assert np.array_equal(got_eng, want.astype(np.float16)) or \
+        np.abs(got_eng.astype(np.float32) - want).max() <= 2.0 ** -11 * np.abs(want).max()
+    assert np.abs(want - src).max() < (0.2 if name.startswith("q4") else 0.1)   # it is a quantisation of src

@@ -38,9 +38,9 @@ def model_path(config: str, ftype: str = "f16", seed: int = 0) -> str:
         gf.write_synthetic(tmp, config, 1 if ftype == "f16" else 0, seed=seed)
     elif ftype == "bf16w":  # bf16-rounded weights stored as f32 (SURVEY.md 8c, bf16 config oracle)
         gf.write_synthetic(tmp, config, 0, seed=seed, round_bf16=True)
-    elif ftype == "q8_0":
+    elif ftype in gf.QUANT_NAMES:
         from oracle import ref
-        subprocess.check_call([ref.QUANTIZE_BIN, model_path(config, "f16", seed), tmp, "8"],
+        subprocess.check_call([ref.QUANTIZE_BIN, model_path(config, "f16", seed), tmp, str(gf.QUANT_NAMES[ftype])],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     else:
         raise ValueError(ftype)

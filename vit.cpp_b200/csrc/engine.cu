@@ -197,21 +197,74 @@ int upload_f32(vitb200_engine *e, const vitb200_tensor *t, int n, const std::str
 uint16_t host_f32_to_f16(float f) { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
 float host_f16_to_f32(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
 
+// ggml block formats of 32 weights (ggml-quants.h:11-47), keyed by ggml_type / file ftype (vit.cpp:645-672).
+size_t quant_block_bytes(int type)
+{
+    switch (type)
+    {
+    case 2: return 18; // q4_0 { f16 d; u8 qs[16] }
+    case 3: return 20; // q4_1 { f16 d; f16 m; u8 qs[16] }
+    case 6: return 22; // q5_0 { f16 d; u8 qh[4]; u8 qs[16] }
+    case 7: return 24; // q5_1 { f16 d; f16 m; u8 qh[4]; u8 qs[16] }
+    case 8: return 34; // q8_0 { f16 d; i8 qs[32] }
+    default: return 0;
+    }
+}
+
+// One block -> 32 floats, the arithmetic of ggml's dequantize_row_q* (ggml-quants.c:1074-1185): low nibbles are elements
+// 0..15, high nibbles 16..31, the q5 formats take their fifth bit from qh; the *_1 formats add the block minimum m.
+void dequant_block(int type, const uint8_t *blk, float *y)
+{
+    uint16_t du = 0, mu = 0;
+    memcpy(&du, blk, 2);
+    const float d = host_f16_to_f32(du);
+    if (type == 8)
+    {
+        const int8_t *q = (const int8_t *)(blk + 2);
+        for (int i = 0; i < 32; ++i) y[i] = d * (float)q[i];
+        return;
+    }
+    const bool has_min = type == 3 || type == 7, five = type == 6 || type == 7;
+    float m = 0.f;
+    if (has_min) { memcpy(&mu, blk + 2, 2); m = host_f16_to_f32(mu); }
+    const uint8_t *p = blk + (has_min ? 4 : 2);
+    uint32_t qh = 0;
+    if (five) { memcpy(&qh, p, 4); p += 4; }
+    for (int j = 0; j < 16; ++j)
+    {
+        int x0 = p[j] & 0x0F, x1 = p[j] >> 4;
+        if (five)
+        {
+            x0 |= (int)(((qh >> j) << 4) & 0x10);
+            x1 |= (int)((qh >> (j + 12)) & 0x10);
+        }
+        if (has_min) { y[j] = (float)x0 * d + m; y[j + 16] = (float)x1 * d + m; }
+        else
+        {
+            const int off = five ? 16 : 8;
+            y[j] = (float)(x0 - off) * d; y[j + 16] = (float)(x1 - off) * d;
+        }
+    }
+}
+
 // Weight matrix [n_out][n_in] -> device f16, row pitch padded to ld (zero filled), + its TMA descriptor.
 //   type 1 (F16): used as stored -- the reference's own operand (ggml.c:1200-1236).
 //   type 8 (Q8_0, blocks of {f16 d; int8 q[32]}, ggml-quants.h:42-46): dequantised once to f16(d * q).  The reference
 //          multiplies int8 x dynamically quantised int8 activations (ggml-quants.c:3521); this W8A16 form stays within the
 //          q8_0 noise floor of that path (1.6e-2 either way); an int8 tensor-core path is future work.
+//   types 2/3/6/7 (Q4_0, Q4_1, Q5_0, Q5_1): same treatment -- dequantised once with ggml's dequantize_row arithmetic and
+//          rounded to f16 (exact for q4_0/q5_0 whenever d*q is a normal f16: a 5-bit integer times an f16).  The reference
+//          dots them against activations quantised on the fly to q8_0/q8_1 (ggml.c type traits vec_dot_type).
 //   type 0 (F32): rounded once to f16 (the reference keeps f32 weights AND f32 activations, ggml.c:1163-1198).
 int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &wname, const std::string &bname,
                   int n_out, int n_in, int ld, Linear *L)
 {
     const vitb200_tensor *w = find_tensor(t, n, wname);
     if (!w) return fail("missing tensor '%s'", wname.c_str());
-    if (w->type != 0 && w->type != 1 && w->type != 8)
-        return fail("tensor '%s': weight type %d is not supported (f32, f16, q8_0 only)", wname.c_str(), w->type);
+    if (w->type != 0 && w->type != 1 && quant_block_bytes(w->type) == 0)
+        return fail("tensor '%s': weight type %d is not supported (f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0 only)", wname.c_str(), w->type);
     if (nelem(w) != (int64_t)n_out * n_in) return fail("tensor '%s' has wrong size: got %lld, expected %lld", wname.c_str(), (long long)nelem(w), (long long)n_out * n_in);
-    if (w->type == 8 && n_in % 32 != 0) return fail("tensor '%s': q8_0 rows must be a multiple of 32", wname.c_str());
+    if (quant_block_bytes(w->type) && n_in % 32 != 0) return fail("tensor '%s': quantised rows must be a multiple of 32", wname.c_str());
     L->n_out = n_out; L->n_in = n_in; L->ld = ld; L->bn = pick_bn(n_out);
     if (dev_alloc(e, &L->w, (size_t)n_out * ld)) return 1;
     CUDA_TRY(cudaMemset(L->w, 0, (size_t)n_out * ld * sizeof(__half)));
@@ -232,14 +285,12 @@ int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::
         else
         {
             const uint8_t *blk = (const uint8_t *)w->data;
-            const size_t nb = conv.size() / 32;
+            const size_t nb = conv.size() / 32, bs = quant_block_bytes(w->type);
+            float y[32];
             for (size_t b = 0; b < nb; ++b)
             {
-                uint16_t du;
-                memcpy(&du, blk + b * 34, 2);
-                const float d = host_f16_to_f32(du);
-                const int8_t *q = (const int8_t *)(blk + b * 34 + 2);
-                for (int i = 0; i < 32; ++i) conv[b * 32 + i] = host_f32_to_f16(d * (float)q[i]);
+                dequant_block(w->type, blk + b * bs, y);
+                for (int i = 0; i < 32; ++i) conv[b * 32 + i] = host_f32_to_f16(y[i]);
             }
         }
         src = conv.data();
@@ -757,6 +808,20 @@ int vitb200_profile_read(vitb200_engine *e, int kind, double *ms_total, int *lau
     *ms_total = ms; *launches = n; *flops_per_launch = fl;
     return 0;
 }
+int vitb200_test_dequant(int type, const void *blocks, int64_t n_blocks, uint16_t *out_f16)
+{
+    const size_t bs = quant_block_bytes(type);
+    if (!bs) return fail("type %d is not a supported block format", type);
+    if (!blocks || !out_f16 || n_blocks < 0) return fail("null argument");
+    float y[32];
+    for (int64_t b = 0; b < n_blocks; ++b)
+    {
+        dequant_block(type, (const uint8_t *)blocks + (size_t)b * bs, y);
+        for (int i = 0; i < 32; ++i) out_f16[b * 32 + i] = host_f32_to_f16(y[i]);
+    }
+    return 0;
+}
+
 void *vitb200_stream(vitb200_engine *e) { return e ? (void *)e->stream : nullptr; }
 
 int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, float *d_probs, float *d_logits,
@@ -1050,7 +1115,10 @@ extern "C" int vitb200_create_from_file(const char *path, int device, int max_ba
         {
         case 0: ft.nbytes = (size_t)ne_total * 4; break;
         case 1: ft.nbytes = (size_t)ne_total * 2; break;
-        case 8: ft.nbytes = (size_t)ne_total / 32 * 34; break;
+        case 2: case 3: case 6: case 7: case 8:
+            if (ft.ne[0] % 32) return fail("tensor '%s': quantised rows must be a multiple of 32", ft.name.c_str());
+            ft.nbytes = (size_t)ne_total / 32 * quant_block_bytes(ft.type);
+            break;
         default: return fail("unknown ftype %d in model file (tensor '%s')", ft.type, ft.name.c_str());
         }
         if (off + ft.nbytes > fsize) return fail("tensor '%s' has wrong size in model file", ft.name.c_str());

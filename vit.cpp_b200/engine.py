@@ -72,6 +72,7 @@ def lib():
         L.vitb200_stream.restype = vp
         L.vitb200_forward_debug.argtypes = [vp, f32p, i32, f32p, f32p, C.POINTER(Taps)]
         L.vitb200_test_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+        L.vitb200_test_dequant.argtypes = [i32, vp, C.c_int64, vp]
         _lib = L
     return _lib
 
@@ -200,6 +201,16 @@ def vit_predict_debug(model: VitModel, images: np.ndarray, tap_layer: int, taps=
     _check(lib().vitb200_forward_debug(model.handle, imgs.ctypes.data, B, probs.ctypes.data, logits.ctypes.data,
                                        C.byref(tp)), "vit_predict_debug")
     return probs, logits, out
+
+
+def test_dequant(ggml_type: int, blocks: np.ndarray) -> np.ndarray:
+    """Host-only: the engine's upload-time conversion of quantised blocks -> float16[n_blocks*32]."""
+    from .ggml_file import QUANT_BLOCK_BYTES
+    raw = np.ascontiguousarray(blocks, np.uint8).reshape(-1)
+    nb = raw.size // QUANT_BLOCK_BYTES[ggml_type]
+    out = np.empty(nb * 32, np.uint16)
+    _check(lib().vitb200_test_dequant(ggml_type, raw.ctypes.data, nb, out.ctypes.data), "vitb200_test_dequant")
+    return out.view(np.float16)
 
 
 def test_gemm(M: int, N: int, K: int, epilogue: int, A16: np.ndarray, W16: np.ndarray, bias: np.ndarray,

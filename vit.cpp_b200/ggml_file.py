@@ -6,7 +6,7 @@ reference ``vit.cpp:308-712`` (``vit_model_load``) parses:
     int32 magic 0x67676d6c ("ggml", ggml.h:211)
     int32 hidden_size, num_hidden_layers, num_attention_heads, num_classes, patch_size, img_size, ftype
     int32 n_labels ; n_labels x { int32 id, int32 len, bytes }
-    per tensor: int32 n_dims, int32 name_len, int32 ftype(0=f32,1=f16,8=q8_0) ;
+    per tensor: int32 n_dims, int32 name_len, int32 ftype(0=f32,1=f16,2=q4_0,3=q4_1,6=q5_0,7=q5_1,8=q8_0) ;
                 n_dims x int32 ne (reversed numpy shape) ; name ; raw data
 
 There are no real timm weights in this environment (no network, no timm), so ``write_synthetic``
@@ -161,8 +161,41 @@ def dequant_q8_0(raw: np.ndarray, n_elem: int) -> np.ndarray:
     return (d * q).reshape(-1)
 
 
+QUANT_BLOCK_BYTES = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}  # ggml-quants.h:11-47, 32 weights per block
+QUANT_NAMES = {"q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_0": 8}
+
+
+def dequant_blocks(ft: int, raw: np.ndarray, n_elem: int) -> np.ndarray:
+    """q4_0 / q4_1 / q5_0 / q5_1 / q8_0 block stream -> f32, the arithmetic of ggml-quants.c dequantize_row_q* (:1074-1185)."""
+    if ft == 8:
+        return dequant_q8_0(raw, n_elem)
+    nb = n_elem // 32
+    blk = raw.reshape(nb, QUANT_BLOCK_BYTES[ft])
+    has_min, five = ft in (3, 7), ft in (6, 7)
+    d = blk[:, 0:2].copy().view(np.float16).astype(np.float32)
+    off = 2
+    m = np.zeros_like(d)
+    if has_min:
+        m = blk[:, 2:4].copy().view(np.float16).astype(np.float32)
+        off = 4
+    lo_hi = np.zeros((nb, 32), np.int32)
+    if five:
+        qh = blk[:, off:off + 4].copy().view(np.uint32).astype(np.int64)  # [nb,1]
+        off += 4
+        j = np.arange(16)
+        lo_hi[:, :16] = ((qh >> j) << 4) & 0x10
+        lo_hi[:, 16:] = (qh >> (j + 12)) & 0x10
+    qs = blk[:, off:off + 16].astype(np.int32)
+    x = np.concatenate([qs & 0x0F, qs >> 4], axis=1) | lo_hi
+    if has_min:
+        y = x.astype(np.float32) * d + m
+    else:
+        y = (x - (16 if five else 8)).astype(np.float32) * d
+    return y.astype(np.float32).reshape(-1)
+
+
 def read(path: str) -> VitFile:
-    """Parse a legacy-ggml ViT file (f32 / f16 / q8_0 tensors)."""
+    """Parse a legacy-ggml ViT file (f32 / f16 / q4_0 / q4_1 / q5_0 / q5_1 / q8_0 tensors)."""
     with open(path, "rb") as f:
         buf = f.read()
     off = 0
@@ -196,12 +229,13 @@ def read(path: str) -> VitFile:
         elif ft == 1:
             arr = np.frombuffer(buf, np.float16, n, off).reshape(shape)
             off += 2 * n
-        elif ft == 8:
-            nbytes = n // QK8_0 * 34
+        elif ft in QUANT_BLOCK_BYTES:
+            nbytes = n // 32 * QUANT_BLOCK_BYTES[ft]
             arr = np.frombuffer(buf, np.uint8, nbytes, off).copy()
             off += nbytes
-            vf.tensors[name + ".q8_0_raw"] = arr
-            arr = dequant_q8_0(arr, n).reshape(shape)
+            if ft == 8:
+                vf.tensors[name + ".q8_0_raw"] = arr
+            arr = dequant_blocks(ft, arr, n).reshape(shape)
         else:
             raise ValueError(f"unsupported tensor ftype {ft}")
         vf.tensors[name] = arr
