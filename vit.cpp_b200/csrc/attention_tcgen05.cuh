@@ -7,7 +7,8 @@
 //   P = softmax    thread = query row = TMEM lane: TRUE row max (2 TMEM passes), e = f16(exp(f16(s/8 - max))) exactly the
 //                  reference's table semantics (ggml.c:10547-10549), un-normalised P written back into the S columns as packed
 //                  f16 (tcgen05.st), l = sum e in f32
-//   O = P V        tcgen05.mma TS: A = P from TMEM, B = V (NKP x 64, MN-major, same TMA tile), D in TMEM; O * (1/l) -> f16
+//   O = P V        tcgen05.mma TS: A = P from TMEM, B = V (NKP x 64, MN-major, same TMA tile), D in TMEM; O * (1/l) -> f16,
+//                  staged in shared memory (SWIZZLE_128B) and written with one TMA store per warp
 //
 // Q, K, V are read straight out of the [tokens][3*D] QKV buffer by TMA (column offset h*64 / D + h*64 / 2D + h*64): no
 // split / transpose copies.  Persistent CTAs (1 per SM), 10 warps: warp 0 TMA producer (2-stage ring over problems),
@@ -20,14 +21,16 @@ namespace vitb200 {
 
 struct AttnTcParams
 {
-    __half *out;  // [T][D]
     int N, D, H;  // tokens per image, hidden, heads
     int n_problems; // B * H
     int NKP;      // keys padded to a multiple of 16
     int n_mtiles; // 1 or 2 query tiles of 128 rows
     int kv_bytes; // NKP * 128 rounded up to 1024
     float scale;  // 1/sqrt(64)
+    long long *trace; // dev only (VITB200_ATTN_TRACE): clock64 stamps of CTA 0, [problem < 16][slot < 32]; NULL in production
 };
+
+#define ATT_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && i < 16 && lane == 0) p.trace[i * 32 + (slot)] = clock64(); } while (0)
 
 constexpr int ATT_TC_THREADS = 320;
 constexpr int ATT_TC_SCOL1 = 224, ATT_TC_OCOL = 448;
@@ -37,13 +40,14 @@ __device__ __forceinline__ uint32_t att_exp_pair(float x0, float x1, float &lsum
     // e = f16(exp(f32(f16(x))))  (ggml.c:10547-10549), two elements at a time
     const float2 xr = __half22float2(__floats2half2_rn(x0, x1));
     const __half2 e = __floats2half2_rn(ptx::ex2_approx(xr.x * 1.4426950408889634f), ptx::ex2_approx(xr.y * 1.4426950408889634f));
-    const float2 ef = __half22float2(e);
-    lsum += ef.x + ef.y;
+    ptx::add_f32_f16(lsum, __half_as_ushort(__low2half(e)));
+    ptx::add_f32_f16(lsum, __half_as_ushort(__high2half(e)));
     return *reinterpret_cast<const uint32_t *>(&e);
 }
 
 __global__ void __launch_bounds__(ATT_TC_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcParams p)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmO, const AttnTcParams p)
 {
     extern __shared__ uint8_t att_tc_smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(att_tc_smem_raw) + 1023u) & ~1023u;
@@ -52,7 +56,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto sQ = [&](int st, int t) { return smem_base + st * stage_bytes + t * 16384; };
     auto sK = [&](int st) { return smem_base + st * stage_bytes + 2 * 16384; };
     auto sV = [&](int st) { return smem_base + st * stage_bytes + 2 * 16384 + p.kv_bytes; };
-    const uint32_t bars = smem_base + 2 * stage_bytes;
+    const uint32_t stage_out = smem_base + 2 * stage_bytes; // 8 x 4 KB: one 32-row x 128-B SWIZZLE_128B store box per soft-max warp
+    const uint32_t bars = stage_out + 8 * 4096;
     // barriers: load_full[2], load_empty[2], s_full[2], p_ready[2], o_full[2], o_empty[2], tmem ptr
     auto load_full = [&](int s) { return bars + 8u * s; };
     auto load_empty = [&](int s) { return bars + 8u * (2 + s); };
@@ -61,13 +66,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto o_full = [&](int t) { return bars + 8u * (8 + t); };
     auto o_empty = [&](int t) { return bars + 8u * (10 + t); };
     const uint32_t tmem_ptr_addr = bars + 8u * 12;
-    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + 2 * stage_bytes + 8 * 12);
+    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + 2 * stage_bytes + 8 * 4096 + 8 * 12);
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp_idx == 0 && lane == 0)
     {
         ptx::prefetch_tensormap(&tmQ);
         ptx::prefetch_tensormap(&tmKV);
+        ptx::prefetch_tensormap(&tmO);
     }
     if (warp_idx == 1 && lane == 0)
     {
@@ -187,7 +193,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int q = warp_idx & 3;        // TMEM lane quarter
         if (t < p.n_mtiles)
         {
-            const int qrow = t * 128 + q * 32 + lane;          // query index within the image
             const bool warp_valid = (t * 128 + q * 32) < p.N;  // warp owns at least one real query row
             const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + scol[t];
             const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + ATT_TC_OCOL;
@@ -197,8 +202,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
             {
                 const int b = prob / p.H, h = prob - b * p.H;
+                if (q == 0) ATT_TRACE(8 * t + 0);
                 ptx::mbar_wait(s_full(t), i & 1);
                 ptx::tcgen05_fence_after();
+                if (q == 0) ATT_TRACE(8 * t + 1);
                 float lsum = 0.f;
                 if (warp_valid)
                 {
@@ -236,6 +243,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         for (int j = 0; j < 16; ++j)
                             if (n32 * 32 + j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]));
                     }
+                    if (q == 0) ATT_TRACE(8 * t + 2);
                     const float mxs = mx * p.scale; // ggml_scale_inplace (vit.cpp:851-854); exact, scale = 1/8
                     // ---- pass 2: P = f16(exp(f16(s*scale - max))) -> packed f16 into the S columns, l = sum P.
                     // Full (mask-free) chunks go two at a time with four independent partial sums so one warp keeps the
@@ -320,10 +328,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(p_ready(t));
+                if (q == 0) ATT_TRACE(8 * t + 3);
 
                 // ---- O_t = P_t V is complete: drain, release, normalise, store
                 ptx::mbar_wait(o_full(t), i & 1);
                 ptx::tcgen05_fence_after();
+                if (q == 0) ATT_TRACE(8 * t + 4);
                 uint32_t o[64];
                 if (warp_valid)
                 {
@@ -336,10 +346,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(o_empty(t));
-                if (warp_valid && qrow < p.N)
+                if (q == 0) ATT_TRACE(8 * t + 5);
+                if (warp_valid)
                 {
+                    // normalise, f16, into this warp's 32-row x 128-B staging box (16-B chunk j of row r at j ^ (r & 7) =
+                    // SWIZZLE_128B, conflict-free), then ONE TMA store; token rows >= N are clipped by the tensor map
                     const float inv = 1.0f / lsum; // p_i = e_i * (1/sum)  (ggml.c:10556-10558)
-                    uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((size_t)b * p.N + qrow) * p.D + h * 64);
+                    const uint32_t sbox = stage_out + (uint32_t)(warp_idx - 2) * 4096u;
+                    if (lane == 0) ptx::tma_store_wait_read<0>(); // the previous problem's store has left the box
+                    __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                     {
@@ -350,10 +365,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             const __half2 hv = __floats2half2_rn(__uint_as_float(o[j * 8 + 2 * e]) * inv, __uint_as_float(o[j * 8 + 2 * e + 1]) * inv);
                             w[e] = *reinterpret_cast<const uint32_t *>(&hv);
                         }
-                        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                        ptx::st_shared_v4(sbox + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        ptx::tma_store_3d(&tmO, sbox, h * 64, t * 128 + q * 32, b);
+                        ptx::tma_store_commit();
                     }
                 }
             }
+            if (lane == 0) ptx::tma_store_wait_all();
         }
     }
 

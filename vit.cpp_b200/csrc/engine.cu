@@ -78,6 +78,24 @@ int make_tmap_f32_box32(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t
     return 0;
 }
 
+// 3-D f16 view [images][tokens][cols] of a [images*tokens][cols] buffer, box = 64 columns x 32 tokens x 1 image, SWIZZLE_128B:
+// the attention epilogue's store target -- token rows past `tokens` are clipped by the TMA unit instead of spilling into the
+// next image.
+int make_tmap_tokens3d(CUtensorMap *m, const void *ptr, uint64_t images, uint64_t tokens, uint64_t cols)
+{
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {cols, tokens, images};
+    cuuint64_t strides[2] = {cols * 2, tokens * cols * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+    return 0;
+}
+
 int make_tmap(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows)
 {
     PFN_tmapEncodeTiled enc = tmap_encoder();
@@ -127,7 +145,7 @@ struct vitb200_engine
     float *d_img = nullptr, *X = nullptr, *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
     int32_t *d_topk_idx = nullptr;
     __half *A16 = nullptr, *QKV16 = nullptr, *H16 = nullptr, *CLS16 = nullptr, *PA = nullptr;
-    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX, tmQ, tmKV;
+    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX, tmQ, tmKV, tmAO;
     bool attn_tc = false; // tcgen05 attention (N <= 224); longer sequences use the mma.sync two-pass kernel
     int max_k = 16;
     int launches = 0;
@@ -436,13 +454,13 @@ int launch_attention_t(vitb200_engine *e, int B, cudaStream_t s)
 int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
 {
     AttnTcParams p{};
-    p.out = e->A16; p.N = e->N; p.D = e->hp.hidden_size; p.H = e->hp.num_attention_heads;
+    p.N = e->N; p.D = e->hp.hidden_size; p.H = e->hp.num_attention_heads;
     p.n_problems = B * p.H;
     p.NKP = (e->N + 15) / 16 * 16;
     p.n_mtiles = (e->N + 127) / 128;
     p.kv_bytes = (p.NKP * 128 + 1023) / 1024 * 1024;
     p.scale = 1.0f / sqrtf((float)(p.D / p.H));
-    const int smem = 1024 + 2 * (2 * 16384 + 2 * p.kv_bytes) + 256;
+    const int smem = 1024 + 2 * (2 * 16384 + 2 * p.kv_bytes) + 8 * 4096 + 256;
     static int smem_set[64] = {};
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -452,8 +470,32 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
         smem_set[dev & 63] = smem;
     }
     const int grid = p.n_problems < e->num_sms ? p.n_problems : e->num_sms;
-    attention_tc_kernel<<<grid, ATT_TC_THREADS, smem, s>>>(e->tmQ, e->tmKV, p);
+    // dev knob: VITB200_ATTN_TRACE=<file> dumps the clock64 phase stamps of CTA 0 for the first launch of the process
+    static int trace_state = 0; // 0 unknown, 1 armed, 2 done/off
+    const char *trace_path = trace_state == 0 ? getenv("VITB200_ATTN_TRACE") : nullptr;
+    if (trace_state == 0) trace_state = trace_path ? 1 : 2;
+    long long *d_trace = nullptr;
+    if (trace_state == 1)
+    {
+        CUDA_TRY(cudaMalloc(&d_trace, 16 * 32 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(d_trace, 0, 16 * 32 * sizeof(long long)));
+        p.trace = d_trace;
+    }
+    attention_tc_kernel<<<grid, ATT_TC_THREADS, smem, s>>>(e->tmQ, e->tmKV, e->tmAO, p);
     CUDA_TRY(cudaGetLastError());
+    if (d_trace)
+    {
+        std::vector<long long> h(16 * 32);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        if (FILE *f = fopen(getenv("VITB200_ATTN_TRACE"), "w"))
+        {
+            for (int i = 0; i < 16; ++i) { for (int j = 0; j < 32; ++j) fprintf(f, "%lld ", h[i * 32 + j]); fprintf(f, "\n"); }
+            fclose(f);
+        }
+        trace_state = 2;
+    }
     e->launches++;
     return 0;
 }
@@ -738,7 +780,8 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
         {
             const int NKP = (e->N + 15) / 16 * 16;
             if (make_tmap(&e->tmQ, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
-                make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP))
+                make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP) ||
+                make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)e->N, (uint64_t)D))
                 return bail(1);
         }
     }
