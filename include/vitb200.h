@@ -146,6 +146,12 @@ int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, flo
 int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W,
                       const float *bias, const float *resid, float *out);
 
+/* Stand-alone run of one attention kernel (head dim 64) over a fused QKV buffer: qkv = f16 bits [B*N][3*H*64] (what the qkv
+ * GEMM leaves behind, reference vit.cpp:826-846), out = float32 [B*N][H*64] (the merged heads before proj, vit.cpp:860-866).
+ * kernel: 0 = the engine's choice for N, 1 = mma.sync two-pass, 2 = tcgen05 single block (N <= 224), 3 = tcgen05 two sweeps
+ * (224 < N <= 640). */
+int vitb200_test_attention(int device, int kernel, int B, int N, int H, const uint16_t *qkv, float *out);
+
 /* Host-only: the upload-time weight conversion of one quantised tensor, `n_blocks` ggml blocks of 32 weights
  * (type = ggml_type / file ftype: 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0; ggml-quants.h:11-47) -> f16 bits, exactly what
  * vitb200_create stores on the device.  Needs no GPU.  Follows dequantize_row_q* (ggml-quants.c:1074-1185). */

@@ -67,3 +67,40 @@ def test_gemm_linearity_at_full_size():
     for r in (0, 127, 128, 25000, M - 1):
         assert np.array_equal(o1[r].astype(np.int64), A[r].astype(np.int64) @ W1.astype(np.int64).T)
 
+
+
+def _attention_ref(qkv16, B, N, H):
+    """float64 restatement of vit.cpp:826-866 on f16 inputs with the reference soft-max semantics (ggml.c:10533-10558):
+    e = f16(exp(f16(s/8 - max))), p = e * (1/sum e); O = P V."""
+    D = H * 64
+    x = qkv16.astype(np.float64).reshape(B, N, 3, H, 64)
+    q, k, v = x[:, :, 0].transpose(0, 2, 1, 3), x[:, :, 1].transpose(0, 2, 1, 3), x[:, :, 2].transpose(0, 2, 1, 3)
+    s = np.einsum("bhqd,bhkd->bhqk", q, k).astype(np.float32) * np.float32(0.125)
+    z = (s - s.max(-1, keepdims=True)).astype(np.float16).astype(np.float64)
+    e = np.exp(z).astype(np.float16).astype(np.float64)
+    o = np.einsum("bhqk,bhkd->bhqd", e, v) / e.sum(-1, keepdims=True)
+    return o.transpose(0, 2, 1, 3).reshape(B * N, D)
+
+
+ATTN_CASES = [  # (B, N, H, kernel)
+    (3, 17, 2, eng.ATTN_TC), (2, 197, 3, eng.ATTN_TC), (2, 197, 3, eng.ATTN_MMA),
+    (2, 577, 2, eng.ATTN_TC_LONG), (2, 577, 2, eng.ATTN_MMA), (1, 225, 1, eng.ATTN_TC_LONG), (3, 384, 1, eng.ATTN_TC_LONG),
+    (2, 401, 2, eng.ATTN_TC_LONG), (1, 640, 1, eng.ATTN_TC_LONG), (20, 577, 16, eng.ATTN_TC_LONG),
+]
+
+
+@pytest.mark.parametrize("B,N,H,kernel", ATTN_CASES)
+def test_attention_kernels_against_numpy(B, N, H, kernel):
+    """Every attention kernel, alone, on random QKV (scores spread over several units so the soft-max is not flat): agreement with
+    the float64 restatement to f16 output rounding + f32 accumulation noise; the last case runs every CTA through many
+    (image, head) problems (persistent-loop parities, K/V ring reuse)."""
+    rng = np.random.default_rng(N * 131 + H)
+    qkv = rng.normal(0.0, 1.0, (B * N, 3 * H * 64)).astype(np.float32)
+    qkv[:, : H * 64] *= 1.5                       # Q: |s/8| up to ~5
+    qkv16 = qkv.astype(np.float16)
+    out = eng.test_attention(qkv16, B, N, H, kernel)
+    ref = _attention_ref(qkv16, B, N, H)
+    assert np.isfinite(out).all()
+    err = np.abs(out - ref)
+    tol = 2.0 ** -10 * np.abs(ref) + 2e-3 * np.abs(ref).max()
+    assert (err <= tol).all(), (err.max(), np.abs(ref).max(), np.unravel_index(err.argmax(), err.shape))

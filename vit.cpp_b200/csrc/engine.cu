@@ -6,6 +6,7 @@
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "attention_tcgen05.cuh"
+#include "attention_tcgen05_long.cuh"
 #include "preprocess.cuh"
 
 #include <cstdarg>
@@ -39,7 +40,11 @@ int fail(const char *fmt, ...)
     do                                                                                    \
     {                                                                                     \
         cudaError_t e_ = (x);                                                             \
-        if (e_ != cudaSuccess) return fail("%s failed: %s", #x, cudaGetErrorString(e_));  \
+        if (e_ != cudaSuccess)                                                            \
+        {                                                                                 \
+            (void)cudaGetLastError(); /* do not leave it for an unrelated later check */  \
+            return fail("%s failed: %s", #x, cudaGetErrorString(e_));                     \
+        }                                                                                 \
     } while (0)
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -145,8 +150,9 @@ struct vitb200_engine
     float *d_img = nullptr, *X = nullptr, *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
     int32_t *d_topk_idx = nullptr;
     __half *A16 = nullptr, *QKV16 = nullptr, *H16 = nullptr, *CLS16 = nullptr, *PA = nullptr;
-    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX, tmQ, tmKV, tmAO;
-    bool attn_tc = false; // tcgen05 attention (N <= 224); longer sequences use the mma.sync two-pass kernel
+    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX, tmQ, tmKV, tmAO, tmKV64;
+    bool attn_tc = false;      // tcgen05 single-block attention (N <= 224)
+    bool attn_tc_long = false; // tcgen05 two-sweep attention (224 < N <= 640); anything longer uses the mma.sync two-pass kernel
     int max_k = 16;
     int launches = 0;
     int cta_group = 2; // CTAs per tcgen05.mma in the GEMMs (2 = CTA pairs; VITB200_CTA_GROUP=1 selects the 1-CTA kernels)
@@ -182,6 +188,8 @@ int dev_alloc(vitb200_engine *e, T **p, size_t count)
     void *q = nullptr;
     CUDA_TRY(cudaMalloc(&q, count * sizeof(T) + 256));
     e->allocs.push_back(q);
+    // activation rows past the current batch are read (and masked) by the attention tiles: they must never hold NaN bit patterns
+    CUDA_TRY(cudaMemset(q, 0, count * sizeof(T) + 256));
     *p = reinterpret_cast<T *>(q);
     return 0;
 }
@@ -500,9 +508,67 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
     return 0;
 }
 
+int launch_attention_tc_long(vitb200_engine *e, int B, cudaStream_t s)
+{
+    AttnLongParams p{};
+    p.N = e->N; p.D = e->hp.hidden_size; p.H = e->hp.num_attention_heads;
+    p.n_problems = B * p.H;
+    p.NKP = (e->N + 15) / 16 * 16;
+    p.kv_rows = (p.NKP + 63) / 64 * 64;
+    p.n_tiles = (e->N + 127) / 128;
+    {
+        const int chunks = (p.NKP + 31) / 32;    // 32-key chunks; a block holds at most 3 (96 TMEM columns)
+        p.nb = (chunks + 2) / 3;
+        if (p.nb < 4) p.nb = 4;
+        p.nb += p.nb & 1;                        // even: the two warpgroups alternate blocks
+    }
+    p.scale = 1.0f / sqrtf((float)(p.D / p.H));
+    if (p.nb > ATT_LONG_MAX_BLOCKS || (p.NKP + 31) / 32 < p.nb)
+        return fail("attention: %d tokens cannot be cut into 4..%d key blocks", e->N, ATT_LONG_MAX_BLOCKS);
+    for (int j = 0; j < p.nb; ++j) p.key0[j] = att_long_block_key0(p.NKP, p.nb, j);
+    p.key0[p.nb] = p.NKP;
+    const int smem = 1024 + 2 * p.kv_rows * 128 + 2 * 16384 + 4 * 4096 + 2048 + 256;
+    static int smem_set[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (smem > smem_set[dev & 63])
+    {
+        CUDA_TRY(cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set[dev & 63] = smem;
+    }
+    const int grid = p.n_problems < e->num_sms ? p.n_problems : e->num_sms;
+    static int trace_state = 0; // dev knob VITB200_ATTN_TRACE=<file>, first launch of the process only
+    if (trace_state == 0) trace_state = getenv("VITB200_ATTN_TRACE") ? 1 : 2;
+    long long *d_trace = nullptr;
+    if (trace_state == 1)
+    {
+        CUDA_TRY(cudaMalloc(&d_trace, 16 * 32 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(d_trace, 0, 16 * 32 * sizeof(long long)));
+        p.trace = d_trace;
+    }
+    attention_tc_long_kernel<<<grid, ATT_LONG_THREADS, smem, s>>>(e->tmQ, e->tmKV64, e->tmAO, p);
+    CUDA_TRY(cudaGetLastError());
+    if (d_trace)
+    {
+        std::vector<long long> h(16 * 32);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        if (FILE *f = fopen(getenv("VITB200_ATTN_TRACE"), "w"))
+        {
+            for (int i = 0; i < 16; ++i) { for (int j = 0; j < 32; ++j) fprintf(f, "%lld ", h[i * 32 + j]); fprintf(f, "\n"); }
+            fclose(f);
+        }
+        trace_state = 2;
+    }
+    e->launches++;
+    return 0;
+}
+
 int launch_attention(vitb200_engine *e, int B, cudaStream_t s)
 {
     if (e->attn_tc) return launch_attention_tc(e, B, s);
+    if (e->attn_tc_long) return launch_attention_tc_long(e, B, s);
     const int qtiles = (e->N + 15) / 16;
     if (qtiles <= 4) return launch_attention_t<4>(e, B, s);
     if (qtiles <= 14) return launch_attention_t<7>(e, B, s);
@@ -775,7 +841,16 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
         return bail(1);
     {
         const char *force = getenv("VITB200_ATTENTION"); // bring-up knob: "mma" forces the warp-MMA kernel
-        e->attn_tc = e->N <= 224 && !(force && strcmp(force, "mma") == 0);
+        const bool force_mma = force && strcmp(force, "mma") == 0;
+        e->attn_tc = e->N <= 224 && !force_mma;
+        e->attn_tc_long = e->N > 224 && e->N <= ATT_LONG_MAX_KEYS && !force_mma;
+        if (e->attn_tc_long)
+        {
+            if (make_tmap(&e->tmQ, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
+                make_tmap(&e->tmKV64, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 64) ||
+                make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)e->N, (uint64_t)D))
+                return bail(1);
+        }
         if (e->attn_tc)
         {
             const int NKP = (e->N + 15) / 16 * 16;
@@ -851,6 +926,49 @@ int vitb200_profile_read(vitb200_engine *e, int kind, double *ms_total, int *lau
     *ms_total = ms; *launches = n; *flops_per_launch = fl;
     return 0;
 }
+int vitb200_test_attention(int device, int kernel, int B, int N, int H, const uint16_t *qkv, float *out)
+{
+    if (!qkv || !out || B < 1 || N < 1 || H < 1) return fail("bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: the vit.cpp_b200 forward path has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    vitb200_engine *e = new vitb200_engine();
+    e->device = device;
+    auto bail = [&](int rc) { vitb200_destroy(e); return rc; };
+    e->num_sms = prop.multiProcessorCount;
+    e->N = N; e->hp.hidden_size = H * 64; e->hp.num_attention_heads = H; e->max_batch = B;
+    const int D = H * 64;
+    const uint64_t T = (uint64_t)B * N;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("stream creation failed"));
+    if (dev_alloc(e, &e->QKV16, (size_t)T * 3 * D) || dev_alloc(e, &e->A16, (size_t)T * D)) return bail(1);
+    if (cudaMemcpy(e->QKV16, qkv, (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
+    if (kernel == 0) kernel = N <= 224 ? 2 : (N <= ATT_LONG_MAX_KEYS ? 3 : 1);
+    if (kernel == 2 && N > 224) return bail(fail("tcgen05 single-block attention needs N <= 224"));
+    if (kernel == 3 && (N <= 112 || N > ATT_LONG_MAX_KEYS)) return bail(fail("tcgen05 two-sweep attention needs 112 < N <= %d", ATT_LONG_MAX_KEYS));
+    e->attn_tc = kernel == 2;
+    e->attn_tc_long = kernel == 3;
+    if (kernel >= 2)
+    {
+        const int NKP = (N + 15) / 16 * 16;
+        if (make_tmap(&e->tmQ, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
+            make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)(NKP <= 224 ? NKP : 64)) ||
+            make_tmap(&e->tmKV64, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 64) ||
+            make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)N, (uint64_t)D))
+            return bail(1);
+    }
+    if (launch_attention(e, B, e->stream)) return bail(1);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(fail("attention kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    std::vector<__half> tmp((size_t)T * D);
+    if (cudaMemcpy(tmp.data(), e->A16, tmp.size() * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return bail(fail("D2H failed"));
+    for (size_t i = 0; i < tmp.size(); ++i) out[i] = __half2float(tmp[i]);
+    return bail(0);
+}
+
 int vitb200_test_dequant(int type, const void *blocks, int64_t n_blocks, uint16_t *out_f16)
 {
     const size_t bs = quant_block_bytes(type);

@@ -59,6 +59,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Named barrier among `nthreads` threads of the CTA (id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // Non-blocking probe (no hardware suspend window): for event loops that poll several barriers
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity)
 {

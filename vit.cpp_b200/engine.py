@@ -73,6 +73,7 @@ def lib():
         L.vitb200_forward_debug.argtypes = [vp, f32p, i32, f32p, f32p, C.POINTER(Taps)]
         L.vitb200_test_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         L.vitb200_test_dequant.argtypes = [i32, vp, C.c_int64, vp]
+        L.vitb200_test_attention.argtypes = [i32, i32, i32, i32, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -201,6 +202,17 @@ def vit_predict_debug(model: VitModel, images: np.ndarray, tap_layer: int, taps=
     _check(lib().vitb200_forward_debug(model.handle, imgs.ctypes.data, B, probs.ctypes.data, logits.ctypes.data,
                                        C.byref(tp)), "vit_predict_debug")
     return probs, logits, out
+
+
+ATTN_AUTO, ATTN_MMA, ATTN_TC, ATTN_TC_LONG = 0, 1, 2, 3
+
+
+def test_attention(qkv16: np.ndarray, B: int, N: int, H: int, kernel: int = ATTN_AUTO, device: int = 0) -> np.ndarray:
+    """Stand-alone attention kernel: qkv16 float16 [B*N, 3*H*64] -> float32 [B*N, H*64]."""
+    q = np.ascontiguousarray(qkv16, np.float16).reshape(B * N, 3 * H * 64)
+    out = np.empty((B * N, H * 64), np.float32)
+    _check(lib().vitb200_test_attention(device, kernel, B, N, H, q.ctypes.data, out.ctypes.data), "vitb200_test_attention")
+    return out
 
 
 def test_dequant(ggml_type: int, blocks: np.ndarray) -> np.ndarray:
