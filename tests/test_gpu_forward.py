@@ -112,6 +112,28 @@ def test_long_sequence_geometry_vit_large_384():
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not shipped")
+def test_full_depth_vit_large_384_bf16_weights_vs_live_reference():
+    """BASELINE.json configs[2] at its real size (ViT-L/16-384: 24 layers, hidden 1024, 577 tokens, bf16-representable weights in
+    the f32 container): one image through the UNMODIFIED reference on the host cores against the engine, plus batch-position
+    invariance of the engine at a batch that makes every attention CTA loop over several heads."""
+    path = model_path("large384", "bf16w")
+    rm = ref.RefModel(path)
+    m = eng.vit_model_load(path, 0, 12)
+    imgs = gf.synthetic_images(12, m.img_size, seed=31)
+    p_ref, l_ref = rm.predict(imgs[5], n_threads=32)
+    rm.close()
+    probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
+    re = np.abs(logits[5] - l_ref).max() / np.abs(l_ref).max()
+    assert re <= 4e-3, re       # f16 activations vs the reference's f32 activations over 24 layers (tiny, 12 layers: <= 2.5e-3)
+    assert np.linalg.norm(logits[5] - l_ref) <= 2.5e-3 * np.linalg.norm(l_ref)
+    assert idx[5, 0] == l_ref.argmax()
+    alone = eng.vit_predict(m, imgs[5:6], 5, want_logits=True)
+    assert np.array_equal(alone[3][0], logits[5])
+    assert np.isfinite(logits).all()
+    m.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not shipped")
 def test_bf16_weights_in_f32_container_vs_reference_f32_path():
     """BASELINE.json configs[2] weight format: the reference has no bf16 type, so the oracle is its f32
     path on a file of bf16-representable f32 weights (f16 patch kernel).  The engine rounds f32 weights to f16 at upload,
