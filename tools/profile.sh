@@ -16,3 +16,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:atte
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:layernorm -s 5 -c 1 \
     -o gpurun_out/prof_ln_${TAG} -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_ln_${TAG}.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+# the two-sweep attention kernel (ViT-L/16-384 geometry: 577 tokens, 16 heads) on its own
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc_long -c 1 \
+    -o gpurun_out/prof_attn_long_${TAG} -f python tools/run_attn_long.py > gpurun_out/ncu_attn_long_${TAG}.log 2>&1
+ls -la gpurun_out/*.ncu-rep
