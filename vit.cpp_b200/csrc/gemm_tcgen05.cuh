@@ -76,13 +76,13 @@ struct GemmCfg
 
 // GELU, tanh form (the reference's formula, ggml.c:1418-1424) on an f16-valued input, evaluated in f32 as
 //   0.5 x (1 + tanh(u)) = x / (1 + e^{-2u}),   u = sqrt(2/pi) x (1 + 0.044715 x^2)
-// (algebraically identical; 6 FMA-pipe ops + MUFU.EX2 + MUFU.RCP, relative error ~3e-7, i.e. the f16 rounding the caller
+// (algebraically identical; 5 FMA-pipe ops + MUFU.EX2 + MUFU.RCP, relative error ~3e-7, i.e. the f16 rounding the caller
 // applies next (table semantics, ggml.c:2197) differs from the host table in well under 0.1 % of inputs, by one ulp).
 __device__ __forceinline__ float gelu_tanh_f32(float x)
 {
-    const float inner = fmaf(0.044715f * x, x, 1.0f);
-    const float t = x * inner;                                   // u / sqrt(2/pi)
-    const float e = ptx::ex2_approx(t * -2.3022081981625516f);   // e^{-2u}: -2 * sqrt(2/pi) * log2(e)
+    // -2u log2(e) = x (k0 + k1 x^2), k0 = -2 sqrt(2/pi) log2(e), k1 = 0.044715 k0: FMUL, FFMA, FMUL, EX2, FADD, RCP, FMUL
+    const float w = fmaf(x * x, -0.10294323958083856f, -2.3022081981625516f);
+    const float e = ptx::ex2_approx(x * w);                      // e^{-2u}
     return x * ptx::rcp_approx(1.0f + e);
 }
 
