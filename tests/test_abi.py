@@ -36,10 +36,14 @@ def test_no_cpu_fallback_without_gpu():
 def test_loader_rejects_bad_files(tmp_path):
     import torch
     bad = tmp_path / "bad.gguf"
-    bad.write_bytes(b"GGUF" + b"\0" * 64)  # real-GGUF magic is NOT what the reference loads
+    bad.write_bytes(b"GGJT" + b"\0" * 64)  # neither the legacy "ggml" magic (vit.cpp:320-328) nor a GGUF container
     with pytest.raises(eng.VitB200Error) as ei:
         eng.vit_model_load(str(bad))
     assert "bad magic" in str(ei.value) or "no CUDA device" in str(ei.value)
+    bad.write_bytes(b"GGUF" + b"\0" * 64)  # GGUF magic, garbage behind it: rejected by the container parser (host side, no GPU needed)
+    with pytest.raises(eng.VitB200Error) as ei:
+        eng.vit_model_load(str(bad))
+    assert "invalid GGUF" in str(ei.value)
     with pytest.raises(eng.VitB200Error):
         eng.vit_model_load(str(tmp_path / "missing.gguf"))
 
@@ -52,3 +56,24 @@ def test_product_path_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle/vit_oracle.c vo_taps", ""), f"{f} mentions the oracle"
+
+
+def test_gguf_container_is_parsed_on_the_host(tmp_path):
+    """A well-formed GGUF file gets through the container parser (hyper-parameters, tensor inventory, alignment) and only then
+    fails for the lack of a GPU; a truncated one is rejected by the parser itself."""
+    import torch
+    from tests.util import gf
+    vf = gf.read(model_path("micro", "f16"))
+    good = tmp_path / "micro.gguf"
+    gf.write_gguf(str(good), vf, "bf16")
+    raw = good.read_bytes()
+    assert raw[:4] == b"GGUF"
+    if not torch.cuda.is_available():
+        with pytest.raises(eng.VitB200Error) as ei:
+            eng.vit_model_load(str(good))
+        assert "no CUDA device" in str(ei.value)
+    cut = tmp_path / "cut.gguf"
+    cut.write_bytes(raw[: len(raw) // 2])
+    with pytest.raises(eng.VitB200Error) as ei:
+        eng.vit_model_load(str(cut))
+    assert "invalid GGUF" in str(ei.value) and "wrong size" in str(ei.value)

@@ -328,3 +328,31 @@ def test_in_process_sharding_over_all_visible_gpus():
     np.testing.assert_allclose(probs[4:], p2, rtol=0, atol=1e-6)
     for m in models:
         m.close()
+
+
+def test_gguf_container_loads_and_matches_the_legacy_file(tmp_path):
+    """the same weights in a true GGUF v3 container (oracle by construction: bit-identical logits to the
+    legacy file the reference loads), including BF16 tensors for the bf16 checkpoint case."""
+    imgs = gf.synthetic_images(3, 64, seed=17)
+    legacy = eng.vit_model_load(model_path("micro", "f16"), 0, 4)
+    want = eng.vit_predict(legacy, imgs, 5, want_logits=True)
+    dst = str(tmp_path / "micro-f16.gguf")
+    gf.legacy_to_gguf(model_path("micro", "f16"), dst)
+    m = eng.vit_model_load(dst, 0, 4)
+    got = eng.vit_predict(m, imgs, 5, want_logits=True)
+    assert np.array_equal(got[3], want[3]) and np.array_equal(got[1], want[1])
+    assert m.label(7) == legacy.label(7) == "LABEL_7"
+    m.close()
+    legacy.close()
+
+    imgs = gf.synthetic_images(2, 224, seed=18)
+    legacy = eng.vit_model_load(model_path("tiny", "bf16w"), 0, 2)   # bf16-representable values in the f32 container
+    want = eng.vit_predict(legacy, imgs, 5, want_logits=True)
+    dst = str(tmp_path / "tiny-bf16.gguf")
+    gf.legacy_to_gguf(model_path("tiny", "bf16w"), dst, "bf16")      # the same values as real BF16 tensors (ggml type 30)
+    assert os.path.getsize(dst) < 0.6 * os.path.getsize(model_path("tiny", "bf16w"))
+    m = eng.vit_model_load(dst, 0, 2)
+    got = eng.vit_predict(m, imgs, 5, want_logits=True)
+    assert np.array_equal(got[3], want[3])
+    m.close()
+    legacy.close()

@@ -70,15 +70,15 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     float *mx_ex = reinterpret_cast<float *>(smem + ex_off);         // [2][128]
     float *l_ex = mx_ex + 256;                                       // [2][128]
     const uint32_t bars = smem_base + ex_off + 2048;
-    // barriers: k_full, kv_empty, v_full, o_full, o_empty, q_full[2], q_empty[2], s_full[4], s_free[4], p_ready[4], tmem ptr
-    const uint32_t k_full = bars, kv_empty = bars + 8, v_full = bars + 16, o_full = bars + 24, o_empty = bars + 32;
+    // barriers: k_full, k_empty, v_full, o_full, o_empty, q_full[2], q_empty[2], s_full[4], s_free[4], p_ready[4], v_empty, tmem ptr
+    const uint32_t k_full = bars, k_empty = bars + 8, v_full = bars + 16, o_full = bars + 24, o_empty = bars + 32, v_empty = bars + 8u * 21;
     auto q_full = [&](int i) { return bars + 8u * (5 + i); };
     auto q_empty = [&](int i) { return bars + 8u * (7 + i); };
     auto s_full = [&](int b) { return bars + 8u * (9 + b); };
     auto s_free = [&](int b) { return bars + 8u * (13 + b); };
     auto p_ready = [&](int b) { return bars + 8u * (17 + b); };
-    const uint32_t tmem_ptr_addr = bars + 8u * 21;
-    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + ex_off + 2048 + 8 * 21);
+    const uint32_t tmem_ptr_addr = bars + 8u * 22;
+    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + ex_off + 2048 + 8 * 22);
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp_idx == 0 && lane == 0)
@@ -91,7 +91,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     {
         ptx::mbar_init(k_full, 1);
         ptx::mbar_init(v_full, 1);
-        ptx::mbar_init(kv_empty, 1);
+        ptx::mbar_init(k_empty, 1);
+        ptx::mbar_init(v_empty, 1);
         for (int i = 0; i < 2; ++i)
         {
             ptx::mbar_init(q_full(i), 1);
@@ -129,7 +130,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             {
                 const int b = prob / p.H, h = prob - b * p.H;
                 const int row0 = b * p.N;
-                ptx::mbar_wait(kv_empty, (ip & 1) ^ 1);
+                ptx::mbar_wait(k_empty, (ip & 1) ^ 1); // K is free once the previous head's last scores are done: this load
+                                                        // overlaps that head's remaining exponentials, P V and epilogue
                 ptx::mbar_arrive_expect_tx(k_full, (uint32_t)(nbox * 8192));
                 for (int x = 0; x < nbox; ++x) ptx::tma_load_2d(sK + x * 8192, &tmKV64, k_full, p.D + h * 64, row0 + x * 64);
                 for (int ti = 0; ti < p.n_tiles; ++ti, ++iq)
@@ -140,6 +142,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     ptx::tma_load_2d(sQ0 + qb * 16384, &tmQ, q_full(qb), h * 64, row0 + ti * 128);
                     if (ti == 0) // V is first needed in sweep B of the first tile: it queues behind K and the first Q tile
                     {
+                        ptx::mbar_wait(v_empty, (ip & 1) ^ 1);
                         ptx::mbar_arrive_expect_tx(v_full, (uint32_t)(nbox * 8192));
                         for (int x = 0; x < nbox; ++x) ptx::tma_load_2d(sV + x * 8192, &tmKV64, v_full, 2 * p.D + h * 64, row0 + x * 64);
                     }
@@ -218,13 +221,17 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                             first = false;
                         }
                         if (j < nb) issue_s(qb, j);
-                        if (j == nb - 1 && ptx::elect_one()) ptx::tcgen05_commit(q_empty(qb)); // every MMA reading this Q tile is issued
+                        if (j == nb - 1 && ptx::elect_one())
+                        {
+                            ptx::tcgen05_commit(q_empty(qb)); // every MMA reading this Q tile is issued
+                            if (ti == p.n_tiles - 1) ptx::tcgen05_commit(k_empty); // ... and, on the head's last tile, every MMA reading K
+                        }
                     }
                     if (ptx::elect_one()) ptx::tcgen05_commit(o_full);
                     __syncwarp();
                     first_tile_of_cta = false;
                 }
-                if (ptx::elect_one()) ptx::tcgen05_commit(kv_empty); // K and V may be overwritten once every MMA of this head has retired
+                if (ptx::elect_one()) ptx::tcgen05_commit(v_empty); // V may be overwritten once every MMA of this head has retired
                 __syncwarp();
             }
         }

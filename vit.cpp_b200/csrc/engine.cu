@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "attention_tcgen05.cuh"
 #include "attention_tcgen05_long.cuh"
+#include "gguf_file.hpp"
 #include "preprocess.cuh"
 
 #include <cstdarg>
@@ -282,13 +283,14 @@ void dequant_block(int type, const uint8_t *blk, float *y)
 //          rounded to f16 (exact for q4_0/q5_0 whenever d*q is a normal f16: a 5-bit integer times an f16).  The reference
 //          dots them against activations quantised on the fly to q8_0/q8_1 (ggml.c type traits vec_dot_type).
 //   type 0 (F32): rounded once to f16 (the reference keeps f32 weights AND f32 activations, ggml.c:1163-1198).
+//   type 30 (BF16, GGUF containers): widened to f32, then as type 0.
 int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &wname, const std::string &bname,
                   int n_out, int n_in, int ld, Linear *L)
 {
     const vitb200_tensor *w = find_tensor(t, n, wname);
     if (!w) return fail("missing tensor '%s'", wname.c_str());
-    if (w->type != 0 && w->type != 1 && quant_block_bytes(w->type) == 0)
-        return fail("tensor '%s': weight type %d is not supported (f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0 only)", wname.c_str(), w->type);
+    if (w->type != 0 && w->type != 1 && w->type != 30 && quant_block_bytes(w->type) == 0)
+        return fail("tensor '%s': weight type %d is not supported (f32, f16, bf16, q4_0, q4_1, q5_0, q5_1, q8_0 only)", wname.c_str(), w->type);
     if (nelem(w) != (int64_t)n_out * n_in) return fail("tensor '%s' has wrong size: got %lld, expected %lld", wname.c_str(), (long long)nelem(w), (long long)n_out * n_in);
     if (quant_block_bytes(w->type) && n_in % 32 != 0) return fail("tensor '%s': quantised rows must be a multiple of 32", wname.c_str());
     L->n_out = n_out; L->n_in = n_in; L->ld = ld; L->bn = pick_bn(n_out);
@@ -307,6 +309,18 @@ int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::
             // raises "illegal instruction" on B200 (tried in round 1), and bf16 activations cost 5e-3 parity.
             const float *f = (const float *)w->data;
             for (size_t i = 0; i < conv.size(); ++i) conv[i] = host_f32_to_f16(f[i]);
+        }
+        else if (w->type == 30)
+        {
+            // BF16 tensors (GGUF containers only): widened to f32 (exact) and rounded to f16 like the f32 case above
+            const uint16_t *h = (const uint16_t *)w->data;
+            for (size_t i = 0; i < conv.size(); ++i)
+            {
+                const uint32_t u = (uint32_t)h[i] << 16;
+                float f;
+                memcpy(&f, &u, 4);
+                conv[i] = host_f32_to_f16(f);
+            }
         }
         else
         {
@@ -1235,6 +1249,30 @@ extern "C" int vitb200_create_from_file(const char *path, int device, int max_ba
     size_t off = 0;
     auto rd32 = [&](int32_t &v) { if (off + 4 > fsize) return false; memcpy(&v, buf.data() + off, 4); off += 4; return true; };
     int32_t magic = 0;
+    if (fsize >= 4 && memcmp(buf.data(), "GGUF", 4) == 0)
+    {
+        // a true GGUF container (the reference itself only reads the legacy format below)
+        GgufModel g;
+        if (!parse_gguf(buf.data(), fsize, g)) return fail("invalid GGUF file '%s': %s", path, g.error.c_str());
+        vitb200_hparams ghp{};
+        ghp.hidden_size = (int32_t)g.hidden_size; ghp.num_hidden_layers = (int32_t)g.num_hidden_layers;
+        ghp.num_attention_heads = (int32_t)g.num_attention_heads; ghp.num_classes = (int32_t)g.num_classes;
+        ghp.patch_size = (int32_t)g.patch_size; ghp.img_size = (int32_t)g.img_size; ghp.ftype = (int32_t)g.ftype; ghp.eps = g.eps;
+        const int expected = 4 + 12 * ghp.num_hidden_layers + 4; // same inventory as the legacy file (vit.cpp:697)
+        if ((int)g.tensors.size() != expected) return fail("model file has %d tensors, but %d tensors were expected", (int)g.tensors.size(), expected);
+        std::vector<vitb200_tensor> gts(g.tensors.size());
+        for (size_t i = 0; i < g.tensors.size(); ++i)
+        {
+            gts[i].name = g.tensors[i].name.c_str();
+            gts[i].data = buf.data() + g.tensors[i].offset;
+            gts[i].type = g.tensors[i].type;
+            gts[i].n_dims = g.tensors[i].n_dims;
+            for (int j = 0; j < 4; ++j) gts[i].ne[j] = g.tensors[i].ne[j];
+        }
+        const int grc = vitb200_create(&ghp, gts.data(), (int)gts.size(), device, max_batch, out);
+        if (grc == 0) (*out)->labels = g.labels;
+        return grc;
+    }
     if (!rd32(magic) || (uint32_t)magic != 0x67676d6cu) return fail("invalid model file '%s' (bad magic)", path); // GGML_FILE_MAGIC, ggml.h:211
     vitb200_hparams hp{};
     int32_t ftype = 0;

@@ -72,8 +72,10 @@ __global__ void layernorm_f16_kernel(const float *__restrict__ x, size_t x_row_s
                                      const float *__restrict__ b, __half *__restrict__ y, int rows, int D, float eps)
 {
     const int warps_per_block = blockDim.x >> 5;
-    const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    // rows are taken LAST FIRST: the producing GEMM wrote them in ascending order, so the tail of X is what the 126 MB L2 still
+    // holds when this kernel starts (and the GEMM that follows, walking up from row 0, meets this kernel's freshest output)
+    const int row = rows - 1 - (blockIdx.x * warps_per_block + (threadIdx.x >> 5));
+    if (row < 0) return;
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * x_row_stride);

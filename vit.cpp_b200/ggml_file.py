@@ -251,3 +251,76 @@ def synthetic_images(batch: int, img_size: int, seed: int = 1234) -> np.ndarray:
     mean = np.array([123.675, 116.280, 103.530], np.float32)
     std = np.array([58.395, 57.120, 57.375], np.float32)
     return ((u8.astype(np.float32) - mean) / std).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# True GGUF (v3) container -- the SURVEY.md 8(f) rank-3 extension read by csrc/gguf_file.hpp (key names documented there).
+GGUF_MAGIC = b"GGUF"
+GGML_TYPE_BF16 = 30  # current ggml; the reference's pinned ggml has no bf16 type
+_GGUF_U32, _GGUF_F32, _GGUF_STR, _GGUF_ARR = 4, 6, 8, 9
+
+
+def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)  # RNE
+
+
+def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def write_gguf(path: str, vf: VitFile, weight_type: str = "keep", alignment: int = 32) -> None:
+    """Write `vf` as GGUF v3.  weight_type: 'keep' (each tensor in its VitFile type; quantised tensors are not supported here),
+    'f16', 'f32' or 'bf16' for the block/head matrices (the patch kernel stays f16, 1-D tensors f32)."""
+    def gstr(b: bytes) -> bytes:
+        return struct.pack("<Q", len(b)) + b
+
+    kv = []
+
+    def kv_u32(k, v):
+        kv.append(gstr(k.encode()) + struct.pack("<II", _GGUF_U32, v))
+
+    kv.append(gstr(b"general.architecture") + struct.pack("<I", _GGUF_STR) + gstr(b"vit"))
+    kv_u32("general.alignment", alignment)
+    kv_u32("general.file_type", vf.ftype)
+    for k, v in (("vit.hidden_size", vf.hidden_size), ("vit.num_hidden_layers", vf.num_hidden_layers),
+                 ("vit.num_attention_heads", vf.num_attention_heads), ("vit.num_classes", vf.num_classes),
+                 ("vit.patch_size", vf.patch_size), ("vit.image_size", vf.img_size)):
+        kv_u32(k, v)
+    kv.append(gstr(b"vit.layer_norm_eps") + struct.pack("<If", _GGUF_F32, 1e-6))
+    if vf.id2label:
+        labels = [vf.id2label.get(i, "").encode() for i in range(max(vf.id2label) + 1)]
+        kv.append(gstr(b"vit.id2label") + struct.pack("<IIQ", _GGUF_ARR, _GGUF_STR, len(labels)) + b"".join(gstr(x) for x in labels))
+
+    names = [n for n in vf.tensors if not n.endswith(".q8_0_raw")]
+    blobs, infos, rel = [], [], 0
+    for name in names:
+        arr = vf.tensors[name]
+        ft = vf.tensor_ftype[name]
+        if ft not in (0, 1):
+            raise ValueError("write_gguf: quantised tensors are not supported")
+        is_mat = arr.ndim >= 2 and name not in ("cls_token", "pos_embed", "patch_embed.proj.bias")
+        if is_mat and name != "patch_embed.proj.weight" and weight_type != "keep":
+            ft = {"f32": 0, "f16": 1, "bf16": GGML_TYPE_BF16}[weight_type]
+        if ft == 0:
+            data = np.ascontiguousarray(arr, np.float32).tobytes()
+        elif ft == 1:
+            data = np.ascontiguousarray(arr, np.float16).tobytes()
+        else:
+            data = f32_to_bf16_bits(np.asarray(arr, np.float32)).tobytes()
+        ne = list(reversed(arr.shape))
+        infos.append(gstr(name.encode()) + struct.pack("<I", len(ne)) + b"".join(struct.pack("<Q", d) for d in ne) +
+                     struct.pack("<IQ", ft, rel))
+        pad = (-len(data)) % alignment
+        blobs.append(data + b"\0" * pad)
+        rel += len(data) + pad
+    head = GGUF_MAGIC + struct.pack("<IQQ", 3, len(names), len(kv)) + b"".join(kv) + b"".join(infos)
+    with open(path, "wb") as f:
+        f.write(head + b"\0" * ((-len(head)) % alignment))
+        for b in blobs:
+            f.write(b)
+
+
+def legacy_to_gguf(src: str, dst: str, weight_type: str = "keep") -> None:
+    """Offline converter (no timm, no torch): legacy-ggml ViT file -> GGUF."""
+    write_gguf(dst, read(src), weight_type)
