@@ -366,11 +366,11 @@ struct ProfScope
     }
 };
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int DEEPK = 0>
 int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
-    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32>;
-    auto kern = gemm_tcgen05_kernel<BN, EPI, 0, CG>;
+    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, DEEPK, CG>;
     // the opt-in to > 48 KB dynamic shared memory is per device (one engine per device, possibly several per process)
     static bool attr_set[64] = {};
     int dev = 0;
@@ -411,6 +411,8 @@ int launch_gemm(vitb200_engine *e, int cg, int bn, int epi, const CUtensorMap &t
         return bn == 256 ? launch_gemm_t<256, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, p, s, num_sms)
                          : launch_gemm_t<128, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, p, s, num_sms);
     }
+    if (epi == EPI_BIAS_RESID_F32 && bn == 256 && cg == 2 && p.K >= 2048) // fc2: shallower residual ring, one more operand stage
+        return launch_gemm_t<256, EPI_BIAS_RESID_F32, 2, 1>(e, tmA, tmB, tmX, p, s, num_sms);
     VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
     VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
     VB_CASE(256, EPI_BIAS_RESID_F32) VB_CASE(128, EPI_BIAS_RESID_F32)

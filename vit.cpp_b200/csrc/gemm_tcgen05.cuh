@@ -50,10 +50,12 @@ constexpr int GEMM_BK = 64;
 // CG = CTAs per MMA (cta_group): 2 = a CTA pair on one TPC computes a 256 x BN tile with M = 256 tcgen05.mma; each CTA
 // stages its own 128 A rows and HALF of the W tile (the pair shares both halves), which halves the per-SM shared-memory
 // traffic of the B operand -- the 1-CTA kernel is shared-memory-bandwidth bound at ~70 % tensor-pipe utilisation.
-template <int BN, bool kResid, int CG, bool kGather = false>
+// kDeepK (fc2, K = 4 D): the main loop of a tile is long, so a shallower residual ring (2 loads in flight per warp) still keeps up
+// and its shared memory buys a fifth operand stage, which is what the tensor pipe is short of there.
+template <int BN, bool kResid, int CG, bool kGather = false, bool kDeepK = false>
 struct GemmCfg
 {
-    static constexpr int kResidRing = 5;
+    static constexpr int kResidRing = kDeepK ? 3 : 5;
     // epilogue warps: 4 for the TMA-ring residual epilogue (HBM-bound), 8 otherwise (two per TMEM lane quarter, splitting
     // the columns) so the ALU-heavy f16 epilogues (bias, GELU, packing) have two warps per SM sub-partition to overlap
     static constexpr int kEpiWarps = kResid ? 4 : 8;
@@ -86,15 +88,15 @@ __device__ __forceinline__ float gelu_tanh_f32(float x)
     return x * ptx::rcp_approx(1.0f + e);
 }
 
-template <int BN, int EPI, int B_FMT, int CG>
-__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32>::kThreads), 1)
+template <int BN, int EPI, int DEEPK, int CG>
+__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0>::kThreads), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const GemmParams p)
 {
     constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32);
     constexpr bool kGather = (EPI == EPI_PATCH_GATHER_F32);
     constexpr bool kPatch = (EPI == EPI_PATCH_F32 || EPI == EPI_PATCH_GATHER_F32);
-    using Cfg = GemmCfg<BN, kResid, CG, kGather>;
+    using Cfg = GemmCfg<BN, kResid, CG, kGather, DEEPK != 0>;
     static_assert(!kGather || (CG == 2 && Cfg::kStages % 3 == 0 && Cfg::kStages >= 3), "gathered patch embedding: CTA pairs, stages in threes");
     constexpr int TILE_M = GEMM_BM * CG; // rows of C per CTA group
     constexpr int kStages = Cfg::kStages;
@@ -210,7 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===================== MMA issuer: whole warp runs the loop (uniform), one elected lane issues =====================
         if (cta_rank == 0) // the leader CTA issues for the whole group
         {
-            constexpr uint32_t idesc = ptx::umma_idesc_f16(TILE_M, BN, /*a=f16*/ 0, B_FMT);
+            constexpr uint32_t idesc = ptx::umma_idesc_f16(TILE_M, BN, /*a=f16*/ 0, /*b=f16*/ 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
