@@ -57,8 +57,21 @@ typedef struct vitb200_tensor
 int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *tensors, int n_tensors, int device, int max_batch,
                    vitb200_engine **out);
 
-/* Same, reading the legacy-ggml model file the reference's vit_model_load parses (vit.cpp:308-712). */
+/* Same, reading the legacy-ggml model file the reference's vit_model_load parses (vit.cpp:308-712), or a true GGUF v2/v3
+ * container with the same tensors (vit.cpp_b200/csrc/gguf_file.hpp). */
 int vitb200_create_from_file(const char *path, int device, int max_batch, vitb200_engine **out);
+
+/* The ViTSTR extension of the reference (extensions/vitstr.cpp): the same encoder on a 1-channel image -- the channel count
+ * is taken from the patch kernel's shape [P, P, C, D] (vitstr.cpp:482; C = 3 in vit.cpp:515) -- whose classifier reads the
+ * first `head_tokens` tokens of every image instead of token 0 (vitstr.cpp:864-903: 25 tokens -> LayerNorm -> head ->
+ * soft-max per token).  head_tokens = 1 is vitb200_create / vitb200_create_from_file.  With head_tokens = n every per-image
+ * output of vitb200_forward* becomes n consecutive rows: probs/logits float32[batch][n][num_classes], top-k [batch][n][k];
+ * images are float32[batch][img][img][C]. */
+int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *tensors, int n_tensors, int device, int max_batch,
+                      int head_tokens, vitb200_engine **out);
+int vitb200_create_from_file_ex(const char *path, int device, int max_batch, int head_tokens, vitb200_engine **out);
+int vitb200_in_chans(const vitb200_engine *e);    /* 3, or 1 for a ViTSTR model */
+int vitb200_head_tokens(const vitb200_engine *e); /* classifier rows per image */
 
 void vitb200_destroy(vitb200_engine *e);
 

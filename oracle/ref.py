@@ -124,3 +124,68 @@ def round_f16(x: np.ndarray) -> np.ndarray:
     y = np.empty_like(x)
     lib().vitref_round_f16(x.ctypes.data, y.ctypes.data, x.size)
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's ViTSTR extension (extensions/vitstr.cpp), its own shared object (oracle/Makefile, oracle/vitstr_harness.cpp)
+VITSTR_LIB_PATH = os.path.join(_HERE, "_ref", "libvitstrref.so")
+_vitstr_lib = None
+
+
+def vitstr_available() -> bool:
+    return os.path.exists(VITSTR_LIB_PATH)
+
+
+def vitstr_lib():
+    global _vitstr_lib
+    if _vitstr_lib is None:
+        L = C.CDLL(VITSTR_LIB_PATH)
+        L.vitstrref_load.restype = C.c_void_p
+        L.vitstrref_load.argtypes = [C.c_char_p]
+        L.vitstrref_hparams.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        L.vitstrref_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.vitstrref_free.argtypes = [C.c_void_p]
+        _vitstr_lib = L
+    return _vitstr_lib
+
+
+class VitstrRefModel:
+    """The extension's vit_model + vit_state, loaded by its own loader (vitstr.cpp:276-683)."""
+
+    SEQ_LEN = 25  # vitstr.cpp:865
+
+    def __init__(self, path: str):
+        with _quiet():
+            self._h = vitstr_lib().vitstrref_load(path.encode())
+        if not self._h:
+            raise RuntimeError(f"reference ViTSTR loader rejected {path}")
+        hp = (C.c_int32 * 7)()
+        vitstr_lib().vitstrref_hparams(self._h, hp)
+        self.hidden, self.layers, self.heads, self.classes, self.patch, self.img, self.ftype = list(hp)
+
+    def predict(self, img_gray: np.ndarray, n_threads: int = 4):
+        """One reference forward on a pre-processed grayscale image [S,S] f32.  Returns (probs, logits) float32[25, classes]."""
+        img = np.ascontiguousarray(img_gray, dtype=np.float32)
+        assert img.size == self.img * self.img, img.shape
+        probs = np.empty((self.SEQ_LEN, self.classes), np.float32)
+        logits = np.empty((self.SEQ_LEN, self.classes), np.float32)
+        with _quiet():
+            rc = vitstr_lib().vitstrref_predict(self._h, img.ctypes.data, n_threads, probs.ctypes.data, logits.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"reference ViTSTR vit_predict returned {rc}")
+        return probs, logits
+
+    def predict_batch(self, imgs: np.ndarray, n_threads: int = 4):
+        ps, ls = zip(*(self.predict(imgs[i], n_threads) for i in range(imgs.shape[0])))
+        return np.stack(ps), np.stack(ls)
+
+    def close(self):
+        if self._h:
+            vitstr_lib().vitstrref_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -32,9 +32,23 @@ def sha256(path):
     return h.hexdigest()
 
 
+VITSTR_CASES = [("vitstr_micro", "f16", 3), ("vitstr_tiny", "f16", 2)]  # the reference's ViTSTR extension (25 x classes per image)
+
+
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     only = set(sys.argv[1:])  # optional: regenerate just these "<config>_<ftype>" fixtures
+    for cfg, ft, n in VITSTR_CASES:
+        if only and f"{cfg}_{ft}" not in only:
+            continue
+        path = model_path(cfg, ft)
+        m = ref.VitstrRefModel(path)
+        imgs = gf.synthetic_gray_images(n, m.img, seed=1234)
+        probs, logits = m.predict_batch(imgs, n_threads=8)
+        np.savez_compressed(os.path.join(out_dir, f"{cfg}_{ft}.npz"), logits=logits, probs=probs,
+                            image_seed=1234, n_images=n, model_sha256=sha256(path))
+        print(cfg, ft, "top1 of tokens 0..4", logits.argmax(-1)[:, :5].tolist(), "sha", sha256(path)[:12])
+        m.close()
     for cfg, ft, n in CASES:
         if only and f"{cfg}_{ft}" not in only:
             continue

@@ -356,3 +356,40 @@ def test_gguf_container_loads_and_matches_the_legacy_file(tmp_path):
     assert np.array_equal(got[3], want[3])
     m.close()
     legacy.close()
+
+
+@pytest.mark.parametrize("cfg", ["vitstr_micro", "vitstr_tiny"])
+def test_vitstr_extension_matches_the_reference(cfg):
+    """the reference's ViTSTR extension (extensions/vitstr.cpp) -- same encoder on a 1-channel image,
+    classifier (LayerNorm + head + soft-max) over the first 25 tokens -- against fixtures generated by the extension itself
+    (tests/golden/make_golden.py) and, when the compiled extension travelled, against a live run.  Same tolerances as the
+    classifier: the 25 x 96 logits of an image are one vector for the relative-error metric."""
+    g = np.load(os.path.join(GOLD, f"{cfg}_f16.npz"))
+    m = eng.vit_model_load(model_path(cfg, "f16"), 0, 4, head_tokens=25)
+    assert (m.in_chans, m.head_tokens) == (1, 25)
+    n = int(g["n_images"])
+    imgs = gf.synthetic_gray_images(n, m.img_size, seed=int(g["image_seed"]))
+    probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
+    assert logits.shape == (n, 25, m.num_classes) and idx.shape == (n, 25, 5)
+    lf, rf = logits.reshape(n, -1), g["logits"].reshape(n, -1)
+    re = np.abs(lf - rf).max(1) / np.abs(rf).max(1)
+    assert np.median(re) <= 1.25e-3 and re.max() <= 2e-3, re
+    assert (np.linalg.norm(lf - rf, axis=1) <= 1.5e-3 * np.linalg.norm(rf, axis=1)).all()
+    # greedy decode = per-token argmax (vitstr.cpp:1029-1052): identical wherever the reference's top-2 gap exceeds the error
+    top2 = np.sort(g["logits"], -1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 2.5 * np.abs(logits - g["logits"]).max(-1)
+    assert clear.mean() > 0.9 and (idx[..., 0] == g["logits"].argmax(-1))[clear].all()
+    dl = np.abs(logits - g["logits"]).max(-1)
+    assert (np.abs(probs - g["probs"]).max(-1) <= 0.55 * dl + 1e-6).all()
+    np.testing.assert_allclose(probs.sum(-1), 1.0, atol=1e-3)
+    if ref.vitstr_available():
+        rm = ref.VitstrRefModel(model_path(cfg, "f16"))
+        extra = gf.synthetic_gray_images(1, m.img_size, seed=77)
+        p_ref, l_ref = rm.predict(extra[0], n_threads=8)
+        got = eng.vit_predict(m, extra, 5, want_logits=True)[3][0]
+        assert np.abs(got - l_ref).max() <= 2e-3 * np.abs(l_ref).max()
+        rm.close()
+    # a 3-channel classifier entry point must refuse this model's input
+    with pytest.raises(eng.VitB200Error):
+        eng.vit_image_preprocess_predict(m, [np.zeros((40, 40, 3), np.uint8)])
+    m.close()

@@ -141,6 +141,8 @@ struct vitb200_engine
     vitb200_hparams hp;
     int device = 0, max_batch = 0, num_sms = 148;
     int N = 0, NP = 0, G = 0, KP = 0, KPp = 0;
+    int C = 3;            // input channels: 3 (vit.cpp) or 1 (ViTSTR extension, vitstr.cpp:713), taken from the patch kernel's shape
+    int head_tokens = 1;  // tokens the classifier head reads per image: 1 (token 0, vit.cpp:910) or 25 (vitstr.cpp:864-903)
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
     // weights
@@ -427,6 +429,15 @@ int launch_patchify(vitb200_engine *e, const float *img, __half *A, int B, cudaS
     const long long total = (long long)B * e->G * e->hp.patch_size * e->G;
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads);
+    if (e->C == 1)
+    {
+        if (e->hp.patch_size != 16 && e->hp.patch_size != 8) return fail("1-channel input: patch size %d not supported (8, 16)", e->hp.patch_size);
+        if (e->hp.patch_size == 16) patchify_f16_kernel<16, 1><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp);
+        else patchify_f16_kernel<8, 1><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp);
+        CUDA_TRY(cudaGetLastError());
+        e->launches++;
+        return 0;
+    }
     switch (e->hp.patch_size)
     {
     case 16: patchify_f16_kernel<16><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
@@ -440,14 +451,16 @@ int launch_patchify(vitb200_engine *e, const float *img, __half *A, int B, cudaS
     return 0;
 }
 
-int launch_layernorm(vitb200_engine *e, const float *x, size_t x_row_stride, const float *w, const float *b, __half *y, int rows, cudaStream_t s)
+int launch_layernorm(vitb200_engine *e, const float *x, size_t x_row_stride, const float *w, const float *b, __half *y, int rows, cudaStream_t s,
+                     int rows_per_group = 0, size_t group_stride = 0)
 {
+    if (rows_per_group <= 0) rows_per_group = rows > 0 ? rows : 1; // one group: plain consecutive rows
     const int D = e->hp.hidden_size;
     const int threads = 256, rows_per_block = threads / 32;
     const int blocks = (rows + rows_per_block - 1) / rows_per_block;
-    if (D <= 4 * 128) layernorm_f16_kernel<4><<<blocks, threads, 0, s>>>(x, x_row_stride, w, b, y, rows, D, e->hp.eps);
-    else if (D <= 8 * 128) layernorm_f16_kernel<8><<<blocks, threads, 0, s>>>(x, x_row_stride, w, b, y, rows, D, e->hp.eps);
-    else if (D <= 16 * 128) layernorm_f16_kernel<16><<<blocks, threads, 0, s>>>(x, x_row_stride, w, b, y, rows, D, e->hp.eps);
+    if (D <= 4 * 128) layernorm_f16_kernel<4><<<blocks, threads, 0, s>>>(x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps);
+    else if (D <= 8 * 128) layernorm_f16_kernel<8><<<blocks, threads, 0, s>>>(x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps);
+    else if (D <= 16 * 128) layernorm_f16_kernel<16><<<blocks, threads, 0, s>>>(x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps);
     else return fail("hidden size %d not supported (max 2048)", D);
     CUDA_TRY(cudaGetLastError());
     e->launches++;
@@ -622,7 +635,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     // patch embedding (vit.cpp:772-797).  P = 16 with CTA pairs: ONE kernel -- the GEMM's A producers gather the f32 pixels
     // straight into the tcgen05 operand tiles (no im2col buffer) and the epilogue adds conv bias + pos_embed and writes token
     // rows.  Other patch sizes: patchify_f16_kernel materialises the f16 patch matrix first.
-    const bool fused_patch = e->hp.patch_size == 16 && e->cta_group == 2;
+    const bool fused_patch = e->hp.patch_size == 16 && e->cta_group == 2 && e->C == 3;
     if (!fused_patch && launch_patchify(e, d_images, PA, B, s)) return 1;
     {
         const int n = B * D, threads = 256;
@@ -690,19 +703,21 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     }
     if (taps && tap_f32(taps->x_final, e->X, (size_t)T * D, s)) return 1;
 
-    // pool (token 0) + final LN + head + soft-max + top-k (vit.cpp:910-933, 1047-1057)
-    if (launch_layernorm(e, e->X, (size_t)N * D, e->norm_w, e->norm_b, e->CLS16, B, s)) return 1;
-    if (taps && tap_f16(taps->final_ln, e->CLS16, (size_t)B * D, s)) return 1;
+    // pool (token 0; the first 25 tokens for ViTSTR, vitstr.cpp:864-883) + final LN + head + soft-max + top-k
+    // (vit.cpp:910-933, 1047-1057); one row of the head GEMM / one soft-max per pooled token
+    const int TH = e->head_tokens, R = B * TH;
+    if (launch_layernorm(e, e->X, (size_t)D, e->norm_w, e->norm_b, e->CLS16, R, s, TH, (size_t)N * D)) return 1;
+    if (taps && tap_f16(taps->final_ln, e->CLS16, (size_t)R * D, s)) return 1;
     float *lg = d_logits ? d_logits : e->d_logits;
     {
         GemmParams p{};
-        p.M = B; p.N = C; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = C;
+        p.M = R; p.N = C; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = C;
         ProfScope ps(e, PK_HEAD, 2.0 * p.M * p.N * p.K, s);
         if (launch_gemm(e, e->cta_group, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, e->tmX, p, s, e->num_sms)) return 1;
     }
     if (d_probs || (k > 0 && (d_topk_idx || d_topk_val)))
     {
-        softmax_topk_kernel<<<B, 256, (size_t)C * sizeof(float), s>>>(lg, d_probs, d_topk_idx, d_topk_val, C, k);
+        softmax_topk_kernel<<<R, 256, (size_t)C * sizeof(float), s>>>(lg, d_probs, d_topk_idx, d_topk_val, C, k);
         CUDA_TRY(cudaGetLastError());
         e->launches++;
     }
@@ -766,6 +781,12 @@ const char *vitb200_last_error(void) { return g_err.c_str(); }
 
 int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, int device, int max_batch, vitb200_engine **out)
 {
+    return vitb200_create_ex(hp, t, n, device, max_batch, 1, out);
+}
+
+int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n, int device, int max_batch, int head_tokens,
+                      vitb200_engine **out)
+{
     if (!hp || !t || !out) return fail("vitb200_create: null argument");
     *out = nullptr;
     int ndev = 0;
@@ -793,7 +814,20 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
     e->G = hp->img_size / P;
     e->NP = e->G * e->G;
     e->N = e->NP + 1;
-    e->KP = 3 * P * P;
+    {
+        // input channels from the patch kernel [P, P, C, D] (vit.cpp:515; C = 1 in vitstr.cpp:482)
+        const vitb200_tensor *pw = find_tensor(t, n, "patch_embed.proj.weight");
+        const int64_t per_c = (int64_t)D * P * P;
+        if (!pw || nelem(pw) % per_c != 0 || (nelem(pw) / per_c != 1 && nelem(pw) / per_c != 3))
+        {
+            delete e;
+            return fail("tensor 'patch_embed.proj.weight' is missing or is not a 1- or 3-channel %dx%d kernel", P, P);
+        }
+        e->C = (int)(nelem(pw) / per_c);
+    }
+    if (head_tokens < 1 || head_tokens > e->N) { const int ntok = e->N; delete e; return fail("head_tokens %d out of range (1..%d)", head_tokens, ntok); }
+    e->head_tokens = head_tokens;
+    e->KP = e->C * P * P;
     e->KPp = (e->KP + 63) / 64 * 64;
     e->cta_group = (getenv("VITB200_CTA_GROUP") && atoi(getenv("VITB200_CTA_GROUP")) == 1) ? 1 : 2;
     e->use_graph = !(getenv("VITB200_GRAPH") && atoi(getenv("VITB200_GRAPH")) == 0);
@@ -828,17 +862,19 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
     // has no K padding; otherwise it gets its own buffer whose zeroed padding columns are never written again.
     const size_t pa_elems = B * e->NP * e->KPp;
     const bool pa_alias = (e->KPp == e->KP) && pa_elems <= h16;
-    if (dev_alloc(e, &e->d_img, B * 3 * hp->img_size * hp->img_size) || dev_alloc(e, &e->X, T * D) ||
+    const size_t R = B * (size_t)e->head_tokens;                        // classifier rows: pooled tokens of all images
+    const size_t img_elems = (size_t)e->C * hp->img_size * hp->img_size; // per image
+    if (dev_alloc(e, &e->d_img, B * img_elems) || dev_alloc(e, &e->X, T * D) ||
         dev_alloc(e, &e->A16, T * D) || dev_alloc(e, &e->QKV16, T * 3 * D) || dev_alloc(e, &e->H16, h16) ||
-        dev_alloc(e, &e->CLS16, B * D) || dev_alloc(e, &e->d_logits, B * hp->num_classes) ||
-        dev_alloc(e, &e->d_probs, B * hp->num_classes) || dev_alloc(e, &e->d_topk_idx, B * e->max_k) ||
-        dev_alloc(e, &e->d_topk_val, B * e->max_k))
+        dev_alloc(e, &e->CLS16, R * D) || dev_alloc(e, &e->d_logits, R * hp->num_classes) ||
+        dev_alloc(e, &e->d_probs, R * hp->num_classes) || dev_alloc(e, &e->d_topk_idx, R * e->max_k) ||
+        dev_alloc(e, &e->d_topk_val, R * e->max_k))
         return bail(1);
     e->d_img_slot[0] = e->d_img; e->d_probs_slot[0] = e->d_probs; e->d_logits_slot[0] = e->d_logits;
     e->d_topk_idx_slot[0] = e->d_topk_idx; e->d_topk_val_slot[0] = e->d_topk_val;
-    if (dev_alloc(e, &e->d_img_slot[1], B * 3 * hp->img_size * hp->img_size) || dev_alloc(e, &e->d_probs_slot[1], B * hp->num_classes) ||
-        dev_alloc(e, &e->d_logits_slot[1], B * hp->num_classes) || dev_alloc(e, &e->d_topk_idx_slot[1], B * e->max_k) ||
-        dev_alloc(e, &e->d_topk_val_slot[1], B * e->max_k))
+    if (dev_alloc(e, &e->d_img_slot[1], B * img_elems) || dev_alloc(e, &e->d_probs_slot[1], R * hp->num_classes) ||
+        dev_alloc(e, &e->d_logits_slot[1], R * hp->num_classes) || dev_alloc(e, &e->d_topk_idx_slot[1], R * e->max_k) ||
+        dev_alloc(e, &e->d_topk_val_slot[1], R * e->max_k))
         return bail(1);
     if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
     for (int i = 0; i < 2; ++i)
@@ -852,7 +888,7 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
         if (cudaMemset(e->PA, 0, pa_elems * sizeof(__half)) != cudaSuccess) return bail(fail("cudaMemset failed"));
     }
     if (make_tmap(&e->tmA_D, e->A16, T, D, D, GEMM_BM) || make_tmap(&e->tmA_H, e->H16, T, 4 * (uint64_t)D, 4 * (uint64_t)D, GEMM_BM) ||
-        make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, B, D, D, GEMM_BM) ||
+        make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, R, D, D, GEMM_BM) ||
         make_tmap_f32_box32(&e->tmX, e->X, T, D, D))
         return bail(1);
     {
@@ -912,6 +948,8 @@ const char *vitb200_label(const vitb200_engine *e, int class_id)
 }
 
 int vitb200_last_launch_count(const vitb200_engine *e) { return e ? e->launches : 0; }
+int vitb200_in_chans(const vitb200_engine *e) { return e ? e->C : 0; }
+int vitb200_head_tokens(const vitb200_engine *e) { return e ? e->head_tokens : 0; }
 
 int vitb200_profile_enable(vitb200_engine *e, int on)
 {
@@ -1022,7 +1060,8 @@ static int forward_enqueue(vitb200_engine *e, const float *images, int batch, fl
     CUDA_TRY(cudaSetDevice(e->device));
     const int sl = (int)(e->submits & 1);
     cudaStream_t s = e->stream, cs = e->copy_stream;
-    const size_t img_elems = (size_t)3 * e->hp.img_size * e->hp.img_size;
+    const size_t img_elems = (size_t)e->C * e->hp.img_size * e->hp.img_size;
+    const size_t rows = (size_t)batch * e->head_tokens; // classifier rows returned
     const int C = e->hp.num_classes;
     if (e->submits >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, e->ev_done[sl], 0)); // slot's previous forward has consumed its inputs/outputs
     CUDA_TRY(cudaMemcpyAsync(e->d_img_slot[sl], images, (size_t)batch * img_elems * sizeof(float), cudaMemcpyHostToDevice, cs));
@@ -1037,10 +1076,10 @@ static int forward_enqueue(vitb200_engine *e, const float *images, int batch, fl
     if (taps ? run_forward(e, e->d_img_slot[sl], batch, dp, e->d_logits_slot[sl], di, dv, kk, s, taps)
              : run_forward_graphed(e, e->d_img_slot[sl], batch, dp, e->d_logits_slot[sl], di, dv, kk, s))
         return 1;
-    if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs_slot[sl], (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits_slot[sl], (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx_slot[sl], (size_t)batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val_slot[sl], (size_t)batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs_slot[sl], rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits_slot[sl], rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx_slot[sl], rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val_slot[sl], rows * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(e->ev_done[sl], s));
     e->submits++;
     return 0;
@@ -1077,8 +1116,9 @@ int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const
     if (!engines || n_engines < 1 || !images) return fail("null argument");
     const vitb200_engine *e0 = engines[0];
     if (!e0) return fail("null engine");
-    const size_t img_elems = (size_t)3 * e0->hp.img_size * e0->hp.img_size;
-    const int C = e0->hp.num_classes;
+    const size_t img_elems = (size_t)e0->C * e0->hp.img_size * e0->hp.img_size;
+    const size_t C = (size_t)e0->hp.num_classes * e0->head_tokens; // output floats per image
+    const size_t kk = (size_t)k * e0->head_tokens;                 // top-k entries per image
     const int base = batch / n_engines, rem = batch % n_engines;
     int begin = 0;
     for (int g = 0; g < n_engines; ++g)
@@ -1086,10 +1126,12 @@ int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const
         const int cnt = base + (g < rem ? 1 : 0);
         if (cnt == 0) continue;
         if (!engines[g]) return fail("null engine %d", g);
-        if (engines[g]->hp.img_size != e0->hp.img_size || engines[g]->hp.num_classes != C) return fail("engine %d holds a different model", g);
+        if (engines[g]->hp.img_size != e0->hp.img_size || engines[g]->hp.num_classes != e0->hp.num_classes || engines[g]->head_tokens != e0->head_tokens ||
+            engines[g]->C != e0->C)
+            return fail("engine %d holds a different model", g);
         if (vitb200_forward_async(engines[g], images + (size_t)begin * img_elems, cnt, probs ? probs + (size_t)begin * C : nullptr,
-                                  logits ? logits + (size_t)begin * C : nullptr, topk_idx ? topk_idx + (size_t)begin * k : nullptr,
-                                  topk_prob ? topk_prob + (size_t)begin * k : nullptr, k))
+                                  logits ? logits + (size_t)begin * C : nullptr, topk_idx ? topk_idx + (size_t)begin * kk : nullptr,
+                                  topk_prob ? topk_prob + (size_t)begin * kk : nullptr, k))
             return 1;
         begin += cnt;
     }
@@ -1117,6 +1159,7 @@ int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const in
                        float *images_f32_out, float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k)
 {
     if (!e || !images || !nx || !ny) return fail("null argument");
+    if (e->C != 3) return fail("vitb200_forward_u8 implements vit_image_preprocess (RGB, vit.cpp:289-305); this model takes %d-channel input", e->C);
     if (batch < 1 || batch > e->max_batch) return fail("batch %d out of range (1..%d)", batch, e->max_batch);
     if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
     CUDA_TRY(cudaSetDevice(e->device));
@@ -1155,10 +1198,11 @@ int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const in
                                 want_topk ? e->d_topk_val : nullptr, want_topk ? k : 0, s))
             return 1;
         e->launches += 1;
-        if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits, (size_t)batch * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx, (size_t)batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val, (size_t)batch * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+        const size_t rows = (size_t)batch * e->head_tokens;
+        if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs, rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits, rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx, rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val, rows * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
@@ -1239,6 +1283,11 @@ struct FileTensor
 
 extern "C" int vitb200_create_from_file(const char *path, int device, int max_batch, vitb200_engine **out)
 {
+    return vitb200_create_from_file_ex(path, device, max_batch, 1, out);
+}
+
+extern "C" int vitb200_create_from_file_ex(const char *path, int device, int max_batch, int head_tokens, vitb200_engine **out)
+{
     if (!path || !out) return fail("null argument");
     std::ifstream fin(path, std::ios::binary);
     if (!fin) return fail("failed to open '%s'", path);
@@ -1271,7 +1320,7 @@ extern "C" int vitb200_create_from_file(const char *path, int device, int max_ba
             gts[i].n_dims = g.tensors[i].n_dims;
             for (int j = 0; j < 4; ++j) gts[i].ne[j] = g.tensors[i].ne[j];
         }
-        const int grc = vitb200_create(&ghp, gts.data(), (int)gts.size(), device, max_batch, out);
+        const int grc = vitb200_create_ex(&ghp, gts.data(), (int)gts.size(), device, max_batch, head_tokens, out);
         if (grc == 0) (*out)->labels = g.labels;
         return grc;
     }
@@ -1338,7 +1387,7 @@ extern "C" int vitb200_create_from_file(const char *path, int device, int max_ba
         ts[i].n_dims = fts[i].n_dims;
         for (int j = 0; j < 4; ++j) ts[i].ne[j] = fts[i].ne[j];
     }
-    int rc = vitb200_create(&hp, ts.data(), (int)ts.size(), device, max_batch, out);
+    int rc = vitb200_create_ex(&hp, ts.data(), (int)ts.size(), device, max_batch, head_tokens, out);
     if (rc == 0) (*out)->labels = labels;
     return rc;
 }

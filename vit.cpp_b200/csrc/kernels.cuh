@@ -12,9 +12,9 @@
 namespace vitb200 {
 
 // ------------------------------------------------------------------------------------------------
-// images [B][S][S][3] f32 (HWC, vit.h:98-103) -> A [B*G*G][ldk] f16, k = c*P*P + ky*P + kx.
-// One thread per (image, patch row py, kernel row ky, patch column px): reads P*3 contiguous floats.
-template <int P>
+// images [B][S][S][C] f32 (HWC, vit.h:98-103; C = 1 for the ViTSTR extension's grayscale input) -> A [B*G*G][ldk] f16,
+// k = c*P*P + ky*P + kx.  One thread per (image, patch row py, kernel row ky, patch column px): reads P*C contiguous floats.
+template <int P, int C = 3>
 __global__ void patchify_f16_kernel(const float *__restrict__ img, __half *__restrict__ A, int B, int S, int G, int ldk)
 {
     const long long total = (long long)B * G * P * G;
@@ -26,12 +26,12 @@ __global__ void patchify_f16_kernel(const float *__restrict__ img, __half *__res
         r /= P;
         const int py = (int)(r % G);
         const int b = (int)(r / G);
-        const float *src = img + (((size_t)b * S + (size_t)(py * P + ky)) * S + (size_t)px * P) * 3;
-        float v[P * 3];
-        if constexpr ((P * 3) % 4 == 0 && (P % 4) == 0)
+        const float *src = img + (((size_t)b * S + (size_t)(py * P + ky)) * S + (size_t)px * P) * C;
+        float v[P * C];
+        if constexpr ((P * C) % 4 == 0 && (P % 4) == 0)
         {
 #pragma unroll
-            for (int i = 0; i < P * 3 / 4; ++i)
+            for (int i = 0; i < P * C / 4; ++i)
             {
                 const float4 f = __ldg(reinterpret_cast<const float4 *>(src) + i);
                 v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
@@ -40,16 +40,16 @@ __global__ void patchify_f16_kernel(const float *__restrict__ img, __half *__res
         else
         {
 #pragma unroll
-            for (int i = 0; i < P * 3; ++i) v[i] = __ldg(src + i);
+            for (int i = 0; i < P * C; ++i) v[i] = __ldg(src + i);
         }
         __half *dst = A + ((size_t)b * G * G + (size_t)py * G + px) * ldk + ky * P;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < C; ++c)
         {
             __half2 *d2 = reinterpret_cast<__half2 *>(dst + c * P * P);
 #pragma unroll
             for (int kx = 0; kx < P; kx += 2)
-                d2[kx >> 1] = __floats2half2_rn(v[kx * 3 + c], v[(kx + 1) * 3 + c]); // RNE, ggml.c:11599
+                d2[kx >> 1] = __floats2half2_rn(v[kx * C + c], v[(kx + 1) * C + c]); // RNE, ggml.c:11599
         }
     }
 }
@@ -68,8 +68,9 @@ __global__ void cls_rows_kernel(float *__restrict__ x, const float *__restrict__
 // ~1e-7 relative), then y = ((x-mean)*scale)*w + b as three separately rounded f32 ops like the
 // reference's NORM, MUL, ADD nodes, then RNE to f16 (the GEMM's src1 conversion, ggml.c:9493-9506).
 template <int MAXV>
-__global__ void layernorm_f16_kernel(const float *__restrict__ x, size_t x_row_stride, const float *__restrict__ w,
-                                     const float *__restrict__ b, __half *__restrict__ y, int rows, int D, float eps)
+__global__ void layernorm_f16_kernel(const float *__restrict__ x, size_t x_row_stride, int rows_per_group, size_t group_stride,
+                                     const float *__restrict__ w, const float *__restrict__ b, __half *__restrict__ y, int rows,
+                                     int D, float eps)
 {
     const int warps_per_block = blockDim.x >> 5;
     // rows are taken LAST FIRST: the producing GEMM wrote them in ascending order, so the tail of X is what the 126 MB L2 still
@@ -78,7 +79,10 @@ __global__ void layernorm_f16_kernel(const float *__restrict__ x, size_t x_row_s
     if (row < 0) return;
     const int lane = threadIdx.x & 31;
     const int nvec = D >> 2;
-    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * x_row_stride);
+    // input row = group g (an image), member t (a token): all T rows are one group for the block LayerNorms; the pooled head
+    // takes the first rows_per_group tokens of every image (token 0: vit.cpp:910; 25 tokens: vitstr.cpp:864-883)
+    const int g = row / rows_per_group, t = row - g * rows_per_group;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)g * group_stride + (size_t)t * x_row_stride);
     float4 v[MAXV];
     float sum = 0.f;
 #pragma unroll

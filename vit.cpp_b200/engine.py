@@ -53,6 +53,10 @@ def lib():
         vp, i32, f32p = C.c_void_p, C.c_int, C.c_void_p
         L.vitb200_last_error.restype = C.c_char_p
         L.vitb200_create_from_file.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
+        L.vitb200_create_from_file_ex.argtypes = [C.c_char_p, i32, i32, i32, C.POINTER(vp)]
+        L.vitb200_create_ex.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(vp)]
+        L.vitb200_in_chans.argtypes = [vp]
+        L.vitb200_head_tokens.argtypes = [vp]
         L.vitb200_create.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
         L.vitb200_destroy.argtypes = [vp]
         L.vitb200_destroy.restype = None
@@ -95,6 +99,8 @@ class VitModel:
         self.hparams = hp
         self.hidden_size, self.num_classes, self.img_size = hp.hidden_size, hp.num_classes, hp.img_size
         self.n_tokens = (hp.img_size // hp.patch_size) ** 2 + 1
+        self.in_chans = lib().vitb200_in_chans(self._h)        # 3, or 1 for a ViTSTR model (vitstr.cpp:713)
+        self.head_tokens = lib().vitb200_head_tokens(self._h)  # classifier rows per image (1, or 25 for ViTSTR)
 
     def label(self, i: int) -> Optional[str]:
         s = lib().vitb200_label(self._h, i)
@@ -119,25 +125,29 @@ class VitModel:
             pass
 
 
-def vit_model_load(fname: str, device: int = 0, max_batch: int = 256) -> VitModel:
-    """reference: bool vit_model_load(const std::string &fname, vit_model &model)  (vit.cpp:308)"""
+def vit_model_load(fname: str, device: int = 0, max_batch: int = 256, head_tokens: int = 1) -> VitModel:
+    """reference: bool vit_model_load(const std::string &fname, vit_model &model)  (vit.cpp:308).  head_tokens = 25 loads a
+    ViTSTR model (reference extensions/vitstr.cpp: 1-channel input, classifier over the first 25 tokens)."""
     h = C.c_void_p()
-    _check(lib().vitb200_create_from_file(fname.encode(), device, max_batch, C.byref(h)), "vit_model_load")
+    _check(lib().vitb200_create_from_file_ex(fname.encode(), device, max_batch, head_tokens, C.byref(h)), "vit_model_load")
     return VitModel(h, device, max_batch)
 
 
 def vit_predict(model: VitModel, images: np.ndarray, topk: int = 5, want_logits: bool = False):
     """Batched reference vit_predict (vit.cpp:1004): images float32[B,S,S,3] (image_f32 layout) on the HOST.
-    Returns (probs[B,C], topk_idx[B,k], topk_prob[B,k]) (+ logits[B,C] if want_logits)."""
+    Returns (probs[B,C], topk_idx[B,k], topk_prob[B,k]) (+ logits[B,C] if want_logits).  For a ViTSTR model (head_tokens = n,
+    images float32[B,S,S] or [B,S,S,1]) every output gains a token axis: probs[B,n,C], topk[B,n,k]."""
     imgs = np.ascontiguousarray(images, dtype=np.float32)
-    if imgs.ndim == 3:
+    ch = model.in_chans
+    if imgs.ndim == (3 if ch == 3 else 2):
         imgs = imgs[None]
     B = imgs.shape[0]
-    assert imgs.shape[1:] == (model.img_size, model.img_size, 3), imgs.shape
-    probs = np.empty((B, model.num_classes), np.float32)
-    logits = np.empty((B, model.num_classes), np.float32) if want_logits else None
-    idx = np.empty((B, topk), np.int32)
-    val = np.empty((B, topk), np.float32)
+    assert imgs.size == B * model.img_size * model.img_size * ch, imgs.shape
+    lead = (B,) if model.head_tokens == 1 else (B, model.head_tokens)
+    probs = np.empty(lead + (model.num_classes,), np.float32)
+    logits = np.empty(lead + (model.num_classes,), np.float32) if want_logits else None
+    idx = np.empty(lead + (topk,), np.int32)
+    val = np.empty(lead + (topk,), np.float32)
     _check(lib().vitb200_forward(model.handle, imgs.ctypes.data, B, probs.ctypes.data,
                                  logits.ctypes.data if want_logits else None, idx.ctypes.data, val.ctypes.data, topk),
            "vit_predict")

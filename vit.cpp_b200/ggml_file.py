@@ -37,7 +37,12 @@ CONFIGS = {
     "micro14": (128, 2, 2, 14, 56),
     # ViT-L/16-384 geometry (hidden 1024, 16 heads, 577 tokens) cut to 2 layers so CPU-side checks stay fast
     "large384x2": (1024, 2, 16, 16, 384),
+    # ViTSTR extension (reference extensions/vitstr.cpp): 1-channel 224x224 input, 96 classes, classifier over 25 tokens
+    "vitstr_micro": (128, 2, 2, 16, 96),
+    "vitstr_tiny": (192, 12, 3, 16, 224),
 }
+IN_CHANS = {"vitstr_micro": 1, "vitstr_tiny": 1}      # default 3
+NUM_CLASSES = {"vitstr_micro": 96, "vitstr_tiny": 96}  # default 1000
 
 
 @dataclass
@@ -59,13 +64,13 @@ class VitFile:
         return g * g + 1
 
 
-def tensor_specs(hidden: int, layers: int, classes: int, patch: int, img: int):
+def tensor_specs(hidden: int, layers: int, classes: int, patch: int, img: int, in_chans: int = 3):
     """(name, numpy shape, is_matrix) in timm state_dict order (convert-pth-to-ggml.py:126-139)."""
     n_tok = (img // patch) ** 2 + 1
     specs = [
         ("cls_token", (1, 1, hidden), False),
         ("pos_embed", (1, n_tok, hidden), False),
-        ("patch_embed.proj.weight", (hidden, 3, patch, patch), True),
+        ("patch_embed.proj.weight", (hidden, in_chans, patch, patch), True),
         ("patch_embed.proj.bias", (hidden,), False),
     ]
     for i in range(layers):
@@ -93,11 +98,11 @@ def tensor_specs(hidden: int, layers: int, classes: int, patch: int, img: int):
     return specs
 
 
-def synth_tensors(hidden, layers, classes, patch, img, seed=0, round_bf16=False):
+def synth_tensors(hidden, layers, classes, patch, img, seed=0, round_bf16=False, in_chans=3):
     """Seeded synthetic weights (SURVEY.md 8c recipe)."""
     rng = np.random.default_rng(seed)
     out = {}
-    for name, shape, is_mat in tensor_specs(hidden, layers, classes, patch, img):
+    for name, shape, is_mat in tensor_specs(hidden, layers, classes, patch, img, in_chans):
         if name == "head.weight":
             w = rng.normal(0.0, 0.2, shape)
         elif name.endswith("norm1.weight") or name.endswith("norm2.weight") or name == "norm.weight":
@@ -129,16 +134,18 @@ def _write_header(f, hp: Tuple[int, ...], ftype: int, classes: int):
         f.write(s)
 
 
-def write_synthetic(path: str, config: str = "tiny", ftype: int = 1, classes: int = 1000, seed: int = 0,
+def write_synthetic(path: str, config: str = "tiny", ftype: int = 1, classes: int = 0, seed: int = 0,
                     round_bf16: bool = False) -> None:
     """Write a synthetic model.  ftype 1: 2-D(+4-D) weights f16, rest f32 (convert-pth-to-ggml.py:143-147).
     ftype 0: everything f32 EXCEPT the patch kernel, which the loader hard-codes as F16 (vit.cpp:515)."""
     hidden, layers, heads, patch, img = CONFIGS[config]
+    in_chans = IN_CHANS.get(config, 3)
+    classes = classes or NUM_CLASSES.get(config, 1000)
     assert ftype in (0, 1)
-    tens = synth_tensors(hidden, layers, classes, patch, img, seed, round_bf16)
+    tens = synth_tensors(hidden, layers, classes, patch, img, seed, round_bf16, in_chans)
     with open(path, "wb") as f:
         _write_header(f, (hidden, layers, heads, patch, img), ftype, classes)
-        for name, shape, is_mat in tensor_specs(hidden, layers, classes, patch, img):
+        for name, shape, is_mat in tensor_specs(hidden, layers, classes, patch, img, in_chans):
             data = tens[name]
             ft = 1 if (is_mat and (ftype == 1 or name == "patch_embed.proj.weight")) else 0
             data = data.astype(np.float16) if ft == 1 else data.astype(np.float32)
@@ -241,6 +248,13 @@ def read(path: str) -> VitFile:
         vf.tensors[name] = arr
         vf.tensor_ftype[name] = ft
     return vf
+
+
+def synthetic_gray_images(batch: int, img_size: int, seed: int = 1234) -> np.ndarray:
+    """float32[B,S,S], values = what the ViTSTR preprocess can emit: (u8/255 - 0.5)*2 (vitstr.cpp:174-175)."""
+    rng = np.random.default_rng(seed)
+    u8 = rng.integers(0, 256, size=(batch, img_size, img_size), dtype=np.uint8)
+    return ((u8.astype(np.float32) / np.float32(255.0) - np.float32(0.5)) * np.float32(2.0)).astype(np.float32)
 
 
 def synthetic_images(batch: int, img_size: int, seed: int = 1234) -> np.ndarray:
