@@ -97,6 +97,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    ptx::grid_dep_launch(); // PDL: the prologue above overlapped the previous kernel's tail
+    ptx::grid_dep_wait();
     const uint32_t scol[2] = {0u, (uint32_t)ATT_TC_SCOL1};
 
     if (warp_idx == 0)

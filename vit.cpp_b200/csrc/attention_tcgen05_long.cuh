@@ -117,6 +117,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    ptx::grid_dep_launch(); // PDL: the prologue above overlapped the previous kernel's tail
+    ptx::grid_dep_wait();
     const int nb = p.nb;
 
     if (warp_idx == 0)

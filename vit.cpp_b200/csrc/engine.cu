@@ -368,6 +368,28 @@ struct ProfScope
     }
 };
 
+// Programmatic dependent launch for the per-layer kernels (GEMMs, attention, LayerNorm): each of them ends its prologue with
+// griddepcontrol.launch_dependents + griddepcontrol.wait (ptx.cuh), so kernel k+1's barrier init / TMEM allocation / descriptor
+// prefetch runs on the SMs kernel k has already left.  VITB200_PDL=0 launches them fully serialised.
+bool pdl_enabled()
+{
+    static const bool on = !(getenv("VITB200_PDL") && atoi(getenv("VITB200_PDL")) == 0);
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BN, int EPI, int CG, int DEEPK = 0>
 int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
@@ -391,11 +413,13 @@ int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &
     cfg.blockDim = dim3((unsigned)Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmX, p));
     if (e) e->launches++;
     return 0;
@@ -458,9 +482,9 @@ int launch_layernorm(vitb200_engine *e, const float *x, size_t x_row_stride, con
     const int D = e->hp.hidden_size;
     const int threads = 256, rows_per_block = threads / 32;
     const int blocks = (rows + rows_per_block - 1) / rows_per_block;
-    if (D <= 4 * 128) layernorm_f16_kernel<4><<<blocks, threads, 0, s>>>(x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps);
-    else if (D <= 8 * 128) layernorm_f16_kernel<8><<<blocks, threads, 0, s>>>(x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps);
-    else if (D <= 16 * 128) layernorm_f16_kernel<16><<<blocks, threads, 0, s>>>(x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps);
+    if (D <= 4 * 128) CUDA_TRY(launch_pdl(layernorm_f16_kernel<4>, dim3(blocks), dim3(threads), 0, s, x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps));
+    else if (D <= 8 * 128) CUDA_TRY(launch_pdl(layernorm_f16_kernel<8>, dim3(blocks), dim3(threads), 0, s, x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps));
+    else if (D <= 16 * 128) CUDA_TRY(launch_pdl(layernorm_f16_kernel<16>, dim3(blocks), dim3(threads), 0, s, x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps));
     else return fail("hidden size %d not supported (max 2048)", D);
     CUDA_TRY(cudaGetLastError());
     e->launches++;
@@ -518,7 +542,7 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
         CUDA_TRY(cudaMemset(d_trace, 0, 16 * 32 * sizeof(long long)));
         p.trace = d_trace;
     }
-    attention_tc_kernel<<<grid, ATT_TC_THREADS, smem, s>>>(e->tmQ, e->tmKV, e->tmAO, p);
+    CUDA_TRY(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATT_TC_THREADS), (size_t)smem, s, e->tmQ, e->tmKV, e->tmAO, p));
     CUDA_TRY(cudaGetLastError());
     if (d_trace)
     {
@@ -575,7 +599,7 @@ int launch_attention_tc_long(vitb200_engine *e, int B, cudaStream_t s)
         CUDA_TRY(cudaMemset(d_trace, 0, 16 * 32 * sizeof(long long)));
         p.trace = d_trace;
     }
-    attention_tc_long_kernel<<<grid, ATT_LONG_THREADS, smem, s>>>(e->tmQ, e->tmKV64, e->tmAO, p);
+    CUDA_TRY(launch_pdl(attention_tc_long_kernel, dim3(grid), dim3(ATT_LONG_THREADS), (size_t)smem, s, e->tmQ, e->tmKV64, e->tmAO, p));
     CUDA_TRY(cudaGetLastError());
     if (d_trace)
     {

@@ -163,6 +163,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads(); // barrier inits visible to the peer before any remote arrive
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    // prologue done (it overlapped the previous kernel's tail under PDL); from here on the kernel touches upstream data
+    ptx::grid_dep_launch();
+    ptx::grid_dep_wait();
 
     if (warp_idx == 0)
     {

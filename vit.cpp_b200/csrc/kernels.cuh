@@ -72,6 +72,8 @@ __global__ void layernorm_f16_kernel(const float *__restrict__ x, size_t x_row_s
                                      const float *__restrict__ w, const float *__restrict__ b, __half *__restrict__ y, int rows,
                                      int D, float eps)
 {
+    ptx::grid_dep_launch(); // PDL: blocks may be resident before the producing GEMM has drained
+    ptx::grid_dep_wait();
     const int warps_per_block = blockDim.x >> 5;
     // rows are taken LAST FIRST: the producing GEMM wrote them in ascending order, so the tail of X is what the 126 MB L2 still
     // holds when this kernel starts (and the GEMM that follows, walking up from row 0, meets this kernel's freshest output)

@@ -59,6 +59,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still draining.  grid_dep_launch() lets OUR successor be scheduled as soon as SMs free up;
+// grid_dep_wait() blocks until the predecessor grid has completed and its memory is visible -- everything before it (barrier
+// init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // Named barrier among `nthreads` threads of the CTA (id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
