@@ -393,3 +393,19 @@ def test_vitstr_extension_matches_the_reference(cfg):
     with pytest.raises(eng.VitB200Error):
         eng.vit_image_preprocess_predict(m, [np.zeros((40, 40, 3), np.uint8)])
     m.close()
+
+
+def test_batch_size_sweep_is_bit_identical_and_stable():
+    """Every batch size from 1 up past the eager/graph switch (8192 tokens = 41 images of 197 tokens) and the persistent-grid
+    boundaries (fewer (image, head) problems than SMs, M tails of the 256-row GEMM tiles): the last image of each batch must
+    come out bit-identical to running it alone, three calls in a row (graph capture on the second, replay on the third)."""
+    m = eng.vit_model_load(model_path("tiny", "f16"), 0, 64)
+    imgs = gf.synthetic_images(64, m.img_size, seed=41)
+    alone = {}
+    for B in (1, 2, 3, 5, 7, 12, 13, 25, 40, 41, 42, 49, 63, 64):
+        want = alone.setdefault(B - 1, eng.vit_predict(m, imgs[B - 1:B], 5, want_logits=True)[3][0])
+        for rep in range(3):
+            p, i, v, l = eng.vit_predict(m, imgs[:B], 5, want_logits=True)
+            assert np.array_equal(l[B - 1], want), (B, rep)
+            assert np.isfinite(l).all() and abs(float(p.sum()) - B) < 1e-2 * B
+    m.close()
