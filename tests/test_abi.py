@@ -77,3 +77,32 @@ def test_gguf_container_is_parsed_on_the_host(tmp_path):
     with pytest.raises(eng.VitB200Error) as ei:
         eng.vit_model_load(str(cut))
     assert "invalid GGUF" in str(ei.value) and "wrong size" in str(ei.value)
+
+
+def test_model_file_parsers_survive_corruption(tmp_path):
+    """Truncations and byte flips of valid GGUF and legacy files must come back as errors (or parse and then stop at the
+    missing GPU), never crash the process: both loaders are bounds-checked host code."""
+    import torch
+    from tests.util import gf
+    rng = np.random.default_rng(5)
+    vf = gf.read(model_path("micro", "f16"))
+    good = tmp_path / "m.gguf"
+    gf.write_gguf(str(good), vf, "keep")
+    for src in (good.read_bytes(), open(model_path("micro", "f16"), "rb").read()):
+        head = 4096  # hyper-parameters, labels / metadata and the first tensor records live here
+        for trial in range(60):
+            raw = bytearray(src)
+            if trial % 2 == 0:
+                raw = raw[: int(rng.integers(0, len(raw)))]
+            else:
+                for _ in range(4):
+                    raw[int(rng.integers(0, min(head, len(raw))))] = int(rng.integers(0, 256))
+            f = tmp_path / f"c{trial}.bin"
+            f.write_bytes(bytes(raw))
+            try:
+                m = eng.vit_model_load(str(f), 0, 2)
+                m.close()            # a flip that left the file valid (only possible with a GPU present)
+                assert torch.cuda.is_available()
+            except eng.VitB200Error:
+                pass
+            f.unlink()
