@@ -156,3 +156,24 @@ def test_block_dequant_matches_ggml(name):
     assert np.array_equal(got_eng, want.astype(np.float16)) or \
         np.abs(got_eng.astype(np.float32) - want).max() <= 2.0 ** -11 * np.abs(want).max()
     assert np.abs(want - src).max() < (0.2 if name.startswith("q4") else 0.1)   # it is a quantisation of src
+
+
+def test_gguf_writer_reader_round_trip(tmp_path):
+    """legacy file -> GGUF (kept types / BF16 matrices) -> read back: hyper-parameters, labels and every tensor survive; BF16 is
+    exact for bf16-representable weights (the bf16w synthetic model) and a 8-bit-mantissa rounding otherwise."""
+    src = gf.read(model_path("micro", "f16"))
+    dst = str(tmp_path / "keep.gguf")
+    gf.write_gguf(dst, src, "keep")
+    back = gf.read_gguf(dst)
+    assert (back.hidden_size, back.num_hidden_layers, back.num_attention_heads, back.num_classes, back.patch_size, back.img_size) == \
+        (src.hidden_size, src.num_hidden_layers, src.num_attention_heads, src.num_classes, src.patch_size, src.img_size)
+    assert back.id2label[5] == src.id2label[5]
+    for name, arr in src.tensors.items():
+        assert back.tensor_ftype[name] == src.tensor_ftype[name] and np.array_equal(back.tensors[name], arr), name
+    srcb = gf.read(model_path("micro", "bf16w"))
+    dstb = str(tmp_path / "bf16.gguf")
+    gf.write_gguf(dstb, srcb, "bf16")
+    backb = gf.read_gguf(dstb)
+    w = "blocks.1.mlp.fc1.weight"
+    assert backb.tensor_ftype[w] == gf.GGML_TYPE_BF16 and np.array_equal(backb.tensors[w], srcb.tensors[w])
+    assert backb.tensor_ftype["patch_embed.proj.weight"] == 1 and backb.tensor_ftype["norm.bias"] == 0

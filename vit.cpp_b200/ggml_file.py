@@ -335,6 +335,70 @@ def write_gguf(path: str, vf: VitFile, weight_type: str = "keep", alignment: int
             f.write(b)
 
 
+def read_gguf(path: str) -> VitFile:
+    """Parse a GGUF v2/v3 ViT container (the Python twin of csrc/gguf_file.hpp, for tooling and tests)."""
+    buf = open(path, "rb").read()
+    off = 0
+
+    def rd(fmt):
+        nonlocal off
+        v = struct.unpack_from("<" + fmt, buf, off)
+        off += struct.calcsize("<" + fmt)
+        return v[0] if len(v) == 1 else v
+
+    def rstr():
+        nonlocal off
+        n = rd("Q")
+        s = buf[off:off + n]
+        off += n
+        return s.decode()
+
+    if buf[:4] != GGUF_MAGIC:
+        raise ValueError("not a GGUF file")
+    off = 4
+    version, n_tensors, n_kv = rd("I"), rd("Q"), rd("Q")
+    if version not in (2, 3):
+        raise ValueError(f"unsupported GGUF version {version}")
+    scalar = {0: "B", 1: "b", 2: "H", 3: "h", 4: "I", 5: "i", 6: "f", 7: "?", 10: "Q", 11: "q", 12: "d"}
+    kv = {}
+    for _ in range(n_kv):
+        key, vt = rstr(), rd("I")
+        if vt == 8:
+            kv[key] = rstr()
+        elif vt == 9:
+            et, cnt = rd("I"), rd("Q")
+            kv[key] = [rstr() if et == 8 else rd(scalar[et]) for _ in range(cnt)]
+        else:
+            kv[key] = rd(scalar[vt])
+    vf = VitFile(kv["vit.hidden_size"], kv["vit.num_hidden_layers"], kv["vit.num_attention_heads"], kv["vit.num_classes"],
+                 kv["vit.patch_size"], kv.get("vit.image_size", kv.get("vit.img_size")), kv.get("general.file_type", 1))
+    vf.id2label = dict(enumerate(kv.get("vit.id2label", [])))
+    align = kv.get("general.alignment", 32)
+    infos = []
+    for _ in range(n_tensors):
+        name, nd = rstr(), rd("I")
+        ne = [rd("Q") for _ in range(nd)]
+        infos.append((name, ne, rd("I"), rd("Q")))
+    data0 = off + (-off) % align
+    for name, ne, ft, rel in infos:
+        shape = tuple(reversed(ne))
+        n = int(np.prod(shape))
+        o = data0 + rel
+        if ft == 0:
+            arr = np.frombuffer(buf, np.float32, n, o).reshape(shape)
+        elif ft == 1:
+            arr = np.frombuffer(buf, np.float16, n, o).reshape(shape)
+        elif ft == GGML_TYPE_BF16:
+            arr = bf16_bits_to_f32(np.frombuffer(buf, np.uint16, n, o)).reshape(shape)
+        elif ft in QUANT_BLOCK_BYTES:
+            arr = dequant_blocks(ft, np.frombuffer(buf, np.uint8, n // 32 * QUANT_BLOCK_BYTES[ft], o).copy(), n).reshape(shape)
+        else:
+            raise ValueError(f"unsupported tensor type {ft}")
+        vf.tensors[name] = arr
+        vf.tensor_ftype[name] = ft
+    return vf
+
+
 def legacy_to_gguf(src: str, dst: str, weight_type: str = "keep") -> None:
     """Offline converter (no timm, no torch): legacy-ggml ViT file -> GGUF."""
     write_gguf(dst, read(src), weight_type)
