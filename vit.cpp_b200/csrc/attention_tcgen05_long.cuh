@@ -33,7 +33,6 @@ struct AttnLongParams
     int nb;          // key blocks (even, 4..ATT_LONG_MAX_BLOCKS) of <= 96 keys
     int key0[9];     // first key of block j (att_long_block_key0), key0[nb] = NKP: read from the constant bank, no divisions on the device
     float scale;     // 1/sqrt(64)
-    long long *trace; // dev only (VITB200_ATTN_TRACE): clock64 stamps of CTA 0, [tile < 16][slot < 32]; NULL in production
 };
 
 
