@@ -32,6 +32,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.vo_create.restype = C.c_void_p
         L.vo_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vo_create_ex.restype = C.c_void_p
+        L.vo_create_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.vo_destroy.argtypes = [C.c_void_p]
         L.vo_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vo_round_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -49,9 +51,12 @@ class OracleModel:
 
     TAP_NAMES = ("embed", "ln1", "qkv", "attn", "x1", "ln2", "h", "x2", "final_ln", "x_final")
 
-    def __init__(self, vf, tensor_specs):
+    def __init__(self, vf, tensor_specs, head_tokens: int = 1):
+        """head_tokens = 25 restates the ViTSTR extension (its channel count comes from the patch kernel's shape)."""
         self.vf = vf
-        specs = tensor_specs(vf.hidden_size, vf.num_hidden_layers, vf.num_classes, vf.patch_size, vf.img_size)
+        self.in_chans = int(vf.tensors["patch_embed.proj.weight"].shape[1])
+        self.head_tokens = head_tokens
+        specs = tensor_specs(vf.hidden_size, vf.num_hidden_layers, vf.num_classes, vf.patch_size, vf.img_size, self.in_chans)
         self._keep = []
         ptrs = (C.c_void_p * len(specs))()
         types = (C.c_int32 * len(specs))()
@@ -64,7 +69,7 @@ class OracleModel:
             types[i] = ft
         hp = (C.c_int32 * 6)(vf.hidden_size, vf.num_hidden_layers, vf.num_attention_heads, vf.num_classes,
                              vf.patch_size, vf.img_size)
-        self._h = lib().vo_create(hp, ptrs, types)
+        self._h = lib().vo_create_ex(hp, ptrs, types, self.in_chans, head_tokens)
         self.classes = vf.num_classes
         self.D = vf.hidden_size
         self.N = vf.n_tokens
@@ -72,8 +77,9 @@ class OracleModel:
     def forward(self, img_hwc: np.ndarray, tap_layer: int | None = None, taps=()):
         """Returns (probs, logits[, {tap: array}])."""
         img = np.ascontiguousarray(img_hwc, np.float32)
-        logits = np.empty(self.classes, np.float32)
-        probs = np.empty(self.classes, np.float32)
+        shape = (self.classes,) if self.head_tokens == 1 else (self.head_tokens, self.classes)
+        logits = np.empty(shape, np.float32)
+        probs = np.empty(shape, np.float32)
         tp = None
         out = {}
         if taps:

@@ -169,6 +169,8 @@ typedef struct {
 
 typedef struct {
     int hidden, layers, heads, classes, patch, img;
+    int in_chans;    /* 3 (vit.cpp:747) or 1 (the ViTSTR extension, vitstr.cpp:713) */
+    int head_tokens; /* tokens the classifier reads: 1 (token 0, vit.cpp:910) or 25 (vitstr.cpp:864-883) */
     float eps;
     const float *cls, *pos, *patch_b, *norm_w, *norm_b, *head_b;
     vo_mat patch_w, head;
@@ -201,16 +203,22 @@ static void mat_free(vo_mat *m) { free(m->w); free(m->qd); free(m->qs); }
 
 /* hp: hidden, layers, heads, classes, patch, img.  tensors/types: 4 + 12*layers + 4 entries in
  * timm state_dict order (see vit.cpp_b200/ggml_file.py tensor_specs; names at vit.cpp:518-579). */
-void *vo_create(const int32_t *hp, const void *const *tensors, const int32_t *types) {
+void *vo_create_ex(const int32_t *hp, const void *const *tensors, const int32_t *types, int in_chans, int head_tokens);
+void *vo_create(const int32_t *hp, const void *const *tensors, const int32_t *types) { return vo_create_ex(hp, tensors, types, 3, 1); }
+
+/* The ViTSTR extension (extensions/vitstr.cpp/vitstr.cpp:684-916) builds the SAME graph with a 1-channel input tensor
+ * (vitstr.cpp:713) and a classifier over the first 25 tokens (vitstr.cpp:864-903): in_chans = 1, head_tokens = 25. */
+void *vo_create_ex(const int32_t *hp, const void *const *tensors, const int32_t *types, int in_chans, int head_tokens) {
     init_tables();
     vo_model *m = (vo_model *)calloc(1, sizeof(vo_model));
     m->hidden = hp[0]; m->layers = hp[1]; m->heads = hp[2]; m->classes = hp[3]; m->patch = hp[4]; m->img = hp[5];
+    m->in_chans = in_chans; m->head_tokens = head_tokens;
     m->eps = 1e-6f; /* vit.h:29; the -e CLI flag never reaches the graph (vit.cpp:808) */
     const int D = m->hidden;
     int t = 0;
     m->cls = (const float *)tensors[t++];
     m->pos = (const float *)tensors[t++];
-    mat_init(&m->patch_w, tensors[t], types[t], D, 3 * m->patch * m->patch); t++;
+    mat_init(&m->patch_w, tensors[t], types[t], D, m->in_chans * m->patch * m->patch); t++;
     m->patch_b = (const float *)tensors[t++];
     m->L = (vo_layer *)calloc((size_t)m->layers, sizeof(vo_layer));
     for (int l = 0; l < m->layers; ++l) {
@@ -358,11 +366,12 @@ typedef struct {
     float *x_final; /* [N][D]  residual stream after the last block */
 } vo_taps;
 
-/* One forward pass of vit_encode_image (vit.cpp:718-941) on one HWC f32 image. */
+/* One forward pass of vit_encode_image (vit.cpp:718-941) on one HWC f32 image ([S][S][in_chans]).  logits_out / probs_out
+ * hold head_tokens x classes values (one soft-max per pooled token). */
 int vo_forward(void *mv, const float *img_hwc, float *logits_out, float *probs_out, const vo_taps *taps) {
     vo_model *m = (vo_model *)mv;
     const int D = m->hidden, H = m->heads, hd = D / H, P = m->patch, S = m->img, G = S / P, NP = G * G, N = NP + 1;
-    const int KP = 3 * P * P;
+    const int CH = m->in_chans, KP = CH * P * P, TH = m->head_tokens;
 
     float *x = (float *)malloc((size_t)N * D * sizeof(float));
     float *cur = (float *)malloc((size_t)N * D * sizeof(float));
@@ -378,12 +387,12 @@ int vo_forward(void *mv, const float *img_hwc, float *logits_out, float *probs_o
         float *col = (float *)malloc((size_t)NP * KP * sizeof(float));
         for (int py = 0; py < G; ++py)
             for (int px = 0; px < G; ++px)
-                for (int c = 0; c < 3; ++c)
+                for (int c = 0; c < CH; ++c)
                     for (int ky = 0; ky < P; ++ky)
                         for (int kx = 0; kx < P; ++kx) {
                             const int iy = py * P + ky, ix = px * P + kx;
                             col[(size_t)(py * G + px) * KP + c * P * P + ky * P + kx] =
-                                round_f16(img_hwc[((size_t)iy * S + ix) * 3 + c]);
+                                round_f16(img_hwc[((size_t)iy * S + ix) * CH + c]);
                         }
         linear(&m->patch_w, m->patch_b, col, NP, x + D); /* f16 x f16: rounding col again is a no-op */
         for (int p = 0; p < NP; ++p)
@@ -422,16 +431,17 @@ int vo_forward(void *mv, const float *img_hwc, float *logits_out, float *probs_o
     }
     if (taps && taps->x_final) memcpy(taps->x_final, x, (size_t)N * D * sizeof(float));
 
-    /* --- pool + head (vit.cpp:910-933): token 0, LN, head linear, f16-table softmax */
-    float *cl = (float *)malloc((size_t)D * sizeof(float));
-    float *lg = (float *)malloc((size_t)m->classes * sizeof(float));
-    layernorm(x, 1, D, m->norm_w, m->norm_b, m->eps, cl);
+    /* --- pool + head (vit.cpp:910-933): token 0 (the first TH tokens for ViTSTR, vitstr.cpp:864-903), LN, head linear,
+     * f16-table softmax per token */
+    float *cl = (float *)malloc((size_t)TH * D * sizeof(float));
+    float *lg = (float *)malloc((size_t)TH * m->classes * sizeof(float));
+    layernorm(x, TH, D, m->norm_w, m->norm_b, m->eps, cl);
     if (taps && taps->final_ln) memcpy(taps->final_ln, cl, (size_t)D * sizeof(float));
-    linear(&m->head, m->head_b, cl, 1, lg);
-    if (logits_out) memcpy(logits_out, lg, (size_t)m->classes * sizeof(float));
+    linear(&m->head, m->head_b, cl, TH, lg);
+    if (logits_out) memcpy(logits_out, lg, (size_t)TH * m->classes * sizeof(float));
     if (probs_out) {
-        softmax_row(lg, m->classes);
-        memcpy(probs_out, lg, (size_t)m->classes * sizeof(float));
+        for (int t = 0; t < TH; ++t) softmax_row(lg + (size_t)t * m->classes, m->classes);
+        memcpy(probs_out, lg, (size_t)TH * m->classes * sizeof(float));
     }
     free(cl); free(lg); free(x); free(cur); free(qkv); free(att); free(hbuf); free(tmp);
     return 0;

@@ -177,3 +177,24 @@ def test_gguf_writer_reader_round_trip(tmp_path):
     w = "blocks.1.mlp.fc1.weight"
     assert backb.tensor_ftype[w] == gf.GGML_TYPE_BF16 and np.array_equal(backb.tensors[w], srcb.tensors[w])
     assert backb.tensor_ftype["patch_embed.proj.weight"] == 1 and backb.tensor_ftype["norm.bias"] == 0
+
+
+@pytest.mark.skipif(not ref.vitstr_available(), reason="oracle/_ref/libvitstrref.so not built")
+@pytest.mark.parametrize("cfg", ["vitstr_micro", "vitstr_tiny"])
+def test_restatement_equals_the_vitstr_extension_bit_for_bit(cfg):
+    """The C restatement with in_chans = 1, head_tokens = 25 against the reference's ViTSTR extension compiled from its own
+    sources (oracle/Makefile: libvitstrref.so): 25 x classes logits and probabilities identical bit for bit, and equal to the
+    committed golden fixture."""
+    path = model_path(cfg, "f16")
+    rm = ref.VitstrRefModel(path)
+    om = rs.OracleModel(gf.read(path), gf.tensor_specs, head_tokens=25)
+    rs.set_threads(8)
+    imgs = gf.synthetic_gray_images(2, rm.img, seed=1234)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{cfg}_f16.npz"))
+    for i in range(2):
+        p_ref, l_ref = rm.predict(imgs[i], n_threads=8)
+        p_o, l_o = om.forward(imgs[i])
+        assert np.array_equal(l_o, l_ref) and np.array_equal(p_o, p_ref)
+        assert np.array_equal(l_ref, g["logits"][i])
+    rm.close()
+    om.close()
