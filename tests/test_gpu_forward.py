@@ -409,3 +409,34 @@ def test_batch_size_sweep_is_bit_identical_and_stable():
             assert np.array_equal(l[B - 1], want), (B, rep)
             assert np.isfinite(l).all() and abs(float(p.sum()) - B) < 1e-2 * B
     m.close()
+
+
+_VITSTR_REF = os.path.join(os.path.dirname(ref.VIT_REF_BIN), "vitstr_ref")
+_VITSTR_B200 = os.path.join(os.path.dirname(ref.VIT_REF_BIN), "vitstr_b200_cli")
+
+
+@pytest.mark.skipif(not (os.path.exists(_VITSTR_REF) and os.path.exists(_VITSTR_B200)), reason="ViTSTR CLI binaries (oracle/_ref) not shipped")
+def test_vitstr_cli_runs_unmodified_on_the_b200_engine(tmp_path):
+    """Drop-in check for the extension at the CLI level: its own main.cpp + loader + stb_image + grayscale preprocess linked
+    against integration/vitstr_predict_b200.cpp + libvitb200.so must decode the same string as the stock extension binary
+    (greedy per-token argmax; random weights leave a few near-ties, so all but at most two of the 24 characters must agree)."""
+    import re
+    import subprocess
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, size=(120, 300, 3), dtype=np.uint8)
+    ppm = tmp_path / "word.ppm"
+    with open(ppm, "wb") as f:
+        f.write(b"P6\n300 120\n255\n" + img.tobytes())
+    model = model_path("vitstr_tiny", "f16")
+
+    def decode(binary):
+        r = subprocess.run([binary, "-m", model, "-i", str(ppm), "-t", "4"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        block = r.stdout.split("------------------")[1].strip().splitlines()
+        return re.findall(r"LABEL_\d+", block[0]), float(block[1].split(":")[1])
+
+    want, want_score = decode(_VITSTR_REF)
+    got, got_score = decode(_VITSTR_B200)
+    assert len(want) == 24 and len(got) == len(want)
+    assert sum(a == b for a, b in zip(got, want)) >= 22, (got, want)
+    assert abs(got_score - want_score) <= 0.011
