@@ -106,3 +106,27 @@ def test_model_file_parsers_survive_corruption(tmp_path):
             except eng.VitB200Error:
                 pass
             f.unlink()
+
+
+def test_gguf_parser_under_address_and_ub_sanitizers(tmp_path):
+    """csrc/gguf_file.hpp is plain host C++: compile it with -fsanitize=address,undefined and throw 4000 truncated / corrupted
+    files at it (tests/cpp/gguf_fuzz.cpp)."""
+    import shutil
+    import subprocess
+    from tests.util import gf
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "gguf_fuzz")
+    r = subprocess.run([gxx, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                        "-I", os.path.join(root, "vit.cpp_b200", "csrc"), os.path.join(root, "tests", "cpp", "gguf_fuzz.cpp"), "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr.lower():
+        pytest.skip("sanitizer runtime not available: " + r.stderr[-200:])
+    assert r.returncode == 0, r.stderr[-2000:]
+    good = str(tmp_path / "m.gguf")
+    gf.write_gguf(good, gf.read(model_path("micro", "f16")), "bf16")
+    r = subprocess.run([exe, good], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    assert "rejected" in r.stdout
