@@ -1,4 +1,4 @@
-// Host-only hardening test for vit.cpp_b200/csrc/gguf_file.hpp: parse a valid GGUF file, then thousands of truncated and
+// Host-only hardening test for vit.cpp_b200/csrc/gguf_file.hpp (GGUF and legacy-ggml parsers): parse a valid file, then thousands of truncated and
 // bit-flipped copies under AddressSanitizer / UBSan (tests/test_abi.py builds and runs this with -fsanitize=address,undefined).
 // Exit code 0 = no memory error and every accepted parse satisfied the parser's own post-conditions.
 #include "gguf_file.hpp"
@@ -8,13 +8,14 @@
 #include <random>
 #include <vector>
 
-int main(int argc, char **argv)
+typedef bool (*parse_fn)(const char *, size_t, vitb200::GgufModel &);
+
+static int fuzz(const char *path, parse_fn parse)
 {
-    if (argc < 2) return 2;
-    std::ifstream f(argv[1], std::ios::binary);
+    std::ifstream f(path, std::ios::binary);
     std::vector<char> good((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     vitb200::GgufModel m;
-    if (!vitb200::parse_gguf(good.data(), good.size(), m)) { fprintf(stderr, "valid file rejected: %s\n", m.error.c_str()); return 1; }
+    if (!parse(good.data(), good.size(), m)) { fprintf(stderr, "valid file rejected: %s\n", m.error.c_str()); return 1; }
     const size_t n_tensors = m.tensors.size();
     std::mt19937 rng(7);
     int accepted = 0, rejected = 0;
@@ -31,7 +32,7 @@ int main(int argc, char **argv)
         char *p = new char[buf.size() ? buf.size() : 1];
         if (!buf.empty()) memcpy(p, buf.data(), buf.size());
         vitb200::GgufModel g;
-        if (vitb200::parse_gguf(p, buf.size(), g))
+        if (parse(p, buf.size(), g))
         {
             ++accepted;
             for (const auto &t : g.tensors)
@@ -40,6 +41,15 @@ int main(int argc, char **argv)
         else ++rejected;
         delete[] p;
     }
-    printf("tensors %zu, accepted %d, rejected %d\n", n_tensors, accepted, rejected);
+    printf("%s: tensors %zu, accepted %d, rejected %d\n", path, n_tensors, accepted, rejected);
     return 0;
+}
+
+// usage: gguf_fuzz <valid.gguf> [<valid legacy-ggml file>]
+int main(int argc, char **argv)
+{
+    if (argc < 2) return 2;
+    int rc = fuzz(argv[1], vitb200::parse_gguf);
+    if (rc == 0 && argc > 2) rc = fuzz(argv[2], vitb200::parse_legacy_ggml);
+    return rc;
 }

@@ -127,6 +127,21 @@ def test_gguf_parser_under_address_and_ub_sanitizers(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     good = str(tmp_path / "m.gguf")
     gf.write_gguf(good, gf.read(model_path("micro", "f16")), "bf16")
-    r = subprocess.run([exe, good], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, good, model_path("micro", "f16")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
-    assert "rejected" in r.stdout
+    assert r.stdout.count("rejected") == 2   # both parsers ran
+
+
+def test_zeroed_hyper_parameters_are_rejected_not_divided_by(tmp_path):
+    """A legacy file whose header says 0 attention heads (or other nonsense) must come back as an error before anything divides
+    by it -- checked ahead of the device probe, so it is testable here."""
+    import struct
+    raw = bytearray(open(model_path("micro", "f16"), "rb").read())
+    for field, value in ((3, 0), (1, 0), (5, 0), (2, -7), (6, 1 << 28)):   # heads, hidden, patch, layers, img (header int32 index)
+        bad = bytearray(raw)
+        struct.pack_into("<i", bad, 4 * field, value)
+        f = tmp_path / f"bad{field}.bin"
+        f.write_bytes(bytes(bad))
+        with pytest.raises(eng.VitB200Error) as ei:
+            eng.vit_model_load(str(f))
+        assert "invalid" in str(ei.value) or "expected" in str(ei.value), str(ei.value)

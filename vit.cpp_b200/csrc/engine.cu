@@ -790,6 +790,12 @@ int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n,
 {
     if (!hp || !t || !out) return fail("vitb200_create: null argument");
     *out = nullptr;
+    // hyper-parameter sanity first (no division by a field a corrupt file may have zeroed; no device needed to reject them)
+    if (hp->hidden_size < 64 || hp->hidden_size > 8192 || hp->num_hidden_layers < 1 || hp->num_hidden_layers > 4096 ||
+        hp->num_attention_heads < 1 || hp->num_attention_heads > 128 || hp->num_classes < 1 || hp->num_classes > (1 << 20) ||
+        hp->patch_size < 1 || hp->patch_size > 64 || hp->img_size < hp->patch_size || hp->img_size > 4096 || n < 1)
+        return fail("invalid hyper-parameters (hidden %d, layers %d, heads %d, classes %d, patch %d, img %d)", hp->hidden_size,
+                    hp->num_hidden_layers, hp->num_attention_heads, hp->num_classes, hp->patch_size, hp->img_size);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("no CUDA device: the vit.cpp_b200 forward path has no CPU fallback");
@@ -1272,15 +1278,6 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
 // Legacy-ggml model file reader (the format reference vit_model_load parses, vit.cpp:308-712; written by
 // convert-pth-to-ggml.py:105-158).  Validation mirrors the reference: magic, known tensor names, element
 // counts; failures return non-zero with a message, never abort.
-namespace {
-struct FileTensor
-{
-    std::string name;
-    int32_t type, n_dims;
-    int64_t ne[4];
-    size_t offset, nbytes;
-};
-} // namespace
 
 extern "C" int vitb200_create_from_file(const char *path, int device, int max_batch, vitb200_engine **out)
 {
@@ -1298,96 +1295,34 @@ extern "C" int vitb200_create_from_file_ex(const char *path, int device, int max
     std::vector<char> buf(fsize);
     fin.read(buf.data(), (std::streamsize)fsize);
     if (!fin) return fail("failed to read '%s'", path);
-    size_t off = 0;
-    auto rd32 = [&](int32_t &v) { if (off + 4 > fsize) return false; memcpy(&v, buf.data() + off, 4); off += 4; return true; };
-    int32_t magic = 0;
-    if (fsize >= 4 && memcmp(buf.data(), "GGUF", 4) == 0)
+    // a true GGUF container or the legacy-ggml file the reference itself reads; both parsers live in
+    // gguf_file.hpp (plain host C++, fuzzed under ASan/UBSan by tests/cpp/gguf_fuzz.cpp) and fill the same structure
+    GgufModel g;
+    const bool is_gguf = fsize >= 4 && memcmp(buf.data(), "GGUF", 4) == 0;
+    if (is_gguf)
     {
-        // a true GGUF container (the reference itself only reads the legacy format below)
-        GgufModel g;
         if (!parse_gguf(buf.data(), fsize, g)) return fail("invalid GGUF file '%s': %s", path, g.error.c_str());
-        vitb200_hparams ghp{};
-        ghp.hidden_size = (int32_t)g.hidden_size; ghp.num_hidden_layers = (int32_t)g.num_hidden_layers;
-        ghp.num_attention_heads = (int32_t)g.num_attention_heads; ghp.num_classes = (int32_t)g.num_classes;
-        ghp.patch_size = (int32_t)g.patch_size; ghp.img_size = (int32_t)g.img_size; ghp.ftype = (int32_t)g.ftype; ghp.eps = g.eps;
-        const int expected = 4 + 12 * ghp.num_hidden_layers + 4; // same inventory as the legacy file (vit.cpp:697)
-        if ((int)g.tensors.size() != expected) return fail("model file has %d tensors, but %d tensors were expected", (int)g.tensors.size(), expected);
-        std::vector<vitb200_tensor> gts(g.tensors.size());
-        for (size_t i = 0; i < g.tensors.size(); ++i)
-        {
-            gts[i].name = g.tensors[i].name.c_str();
-            gts[i].data = buf.data() + g.tensors[i].offset;
-            gts[i].type = g.tensors[i].type;
-            gts[i].n_dims = g.tensors[i].n_dims;
-            for (int j = 0; j < 4; ++j) gts[i].ne[j] = g.tensors[i].ne[j];
-        }
-        const int grc = vitb200_create_ex(&ghp, gts.data(), (int)gts.size(), device, max_batch, head_tokens, out);
-        if (grc == 0) (*out)->labels = g.labels;
-        return grc;
     }
-    if (!rd32(magic) || (uint32_t)magic != 0x67676d6cu) return fail("invalid model file '%s' (bad magic)", path); // GGML_FILE_MAGIC, ggml.h:211
+    else if (!parse_legacy_ggml(buf.data(), fsize, g))
+        return fail("invalid model file '%s' (%s)", path, g.error.c_str());
     vitb200_hparams hp{};
-    int32_t ftype = 0;
-    if (!rd32(hp.hidden_size) || !rd32(hp.num_hidden_layers) || !rd32(hp.num_attention_heads) || !rd32(hp.num_classes) ||
-        !rd32(hp.patch_size) || !rd32(hp.img_size) || !rd32(ftype))
-        return fail("truncated header in '%s'", path);
-    hp.ftype = ftype % 1000; // GGML_QNT_VERSION_FACTOR, vit.cpp:343-354
-    hp.eps = 1e-6f;
-    std::map<int, std::string> labels;
-    int32_t n_labels = 0;
-    if (!rd32(n_labels) || n_labels < 0) return fail("truncated label table in '%s'", path);
-    for (int i = 0; i < n_labels; ++i)
-    {
-        int32_t key = 0, len = 0;
-        if (!rd32(key) || !rd32(len) || len < 0 || off + (size_t)len > fsize) return fail("truncated label table in '%s'", path);
-        labels[key] = std::string(buf.data() + off, (size_t)len);
-        off += (size_t)len;
-    }
-    std::vector<FileTensor> fts;
-    while (off < fsize)
-    {
-        FileTensor ft{};
-        int32_t len = 0;
-        if (!rd32(ft.n_dims) || !rd32(len) || !rd32(ft.type)) return fail("truncated tensor record in '%s'", path);
-        if (ft.n_dims < 1 || ft.n_dims > 4 || len < 0) return fail("corrupt tensor record in '%s'", path);
-        int64_t ne_total = 1;
-        for (int i = 0; i < 4; ++i) ft.ne[i] = 1;
-        for (int i = 0; i < ft.n_dims; ++i)
-        {
-            int32_t d = 0;
-            if (!rd32(d) || d < 1) return fail("corrupt tensor dims in '%s'", path);
-            ft.ne[i] = d;
-            ne_total *= d;
-        }
-        if (off + (size_t)len > fsize) return fail("truncated tensor name in '%s'", path);
-        ft.name.assign(buf.data() + off, (size_t)len);
-        off += (size_t)len;
-        switch (ft.type) // vit.cpp:645-678
-        {
-        case 0: ft.nbytes = (size_t)ne_total * 4; break;
-        case 1: ft.nbytes = (size_t)ne_total * 2; break;
-        case 2: case 3: case 6: case 7: case 8:
-            if (ft.ne[0] % 32) return fail("tensor '%s': quantised rows must be a multiple of 32", ft.name.c_str());
-            ft.nbytes = (size_t)ne_total / 32 * quant_block_bytes(ft.type);
-            break;
-        default: return fail("unknown ftype %d in model file (tensor '%s')", ft.type, ft.name.c_str());
-        }
-        if (off + ft.nbytes > fsize) return fail("tensor '%s' has wrong size in model file", ft.name.c_str());
-        ft.offset = off;
-        off += ft.nbytes;
-        fts.push_back(ft);
-    }
+    auto i32 = [](int64_t v) { return (int32_t)(v < -1 ? -1 : (v > (1 << 30) ? (1 << 30) : v)); }; // out-of-range values stay out of range
+    hp.hidden_size = i32(g.hidden_size); hp.num_hidden_layers = i32(g.num_hidden_layers);
+    hp.num_attention_heads = i32(g.num_attention_heads); hp.num_classes = i32(g.num_classes);
+    hp.patch_size = i32(g.patch_size); hp.img_size = i32(g.img_size); hp.ftype = i32(g.ftype); hp.eps = g.eps;
+    if (hp.num_hidden_layers < 1 || hp.num_hidden_layers > 4096) return fail("invalid model file '%s' (num_hidden_layers %d)", path, hp.num_hidden_layers);
     const int expected = 4 + 12 * hp.num_hidden_layers + 4; // vit.cpp:697
-    if ((int)fts.size() != expected) return fail("model file has %d tensors, but %d tensors were expected", (int)fts.size(), expected);
-    std::vector<vitb200_tensor> ts(fts.size());
-    for (size_t i = 0; i < fts.size(); ++i)
+    if ((int)g.tensors.size() != expected) return fail("model file has %d tensors, but %d tensors were expected", (int)g.tensors.size(), expected);
+    std::vector<vitb200_tensor> ts(g.tensors.size());
+    for (size_t i = 0; i < g.tensors.size(); ++i)
     {
-        ts[i].name = fts[i].name.c_str();
-        ts[i].data = buf.data() + fts[i].offset;
-        ts[i].type = fts[i].type;
-        ts[i].n_dims = fts[i].n_dims;
-        for (int j = 0; j < 4; ++j) ts[i].ne[j] = fts[i].ne[j];
+        ts[i].name = g.tensors[i].name.c_str();
+        ts[i].data = buf.data() + g.tensors[i].offset;
+        ts[i].type = g.tensors[i].type;
+        ts[i].n_dims = g.tensors[i].n_dims;
+        for (int j = 0; j < 4; ++j) ts[i].ne[j] = g.tensors[i].ne[j];
     }
+    const std::map<int, std::string> &labels = g.labels;
     int rc = vitb200_create_ex(&hp, ts.data(), (int)ts.size(), device, max_batch, head_tokens, out);
     if (rc == 0) (*out)->labels = labels;
     return rc;

@@ -156,6 +156,7 @@ inline bool parse_gguf(const char *buf, size_t size, GgufModel &m)
             uint64_t e = 0;
             if (!rd(&e, 8) || e < 1 || e > (1ull << 40)) return fail("corrupt GGUF tensor dims");
             t.ne[d] = (int64_t)e;
+            if (n > (int64_t)(1ull << 40) / (int64_t)e) return fail("corrupt GGUF tensor dims (too many elements)");
             n *= (int64_t)e;
         }
         if (!rd(&type, 4) || !rd(&rel, 8)) return fail("corrupt GGUF tensor info");
@@ -171,6 +172,67 @@ inline bool parse_gguf(const char *buf, size_t size, GgufModel &m)
     {
         t.offset += data0;
         if (t.offset + t.nbytes > size) return fail("tensor '" + t.name + "' has wrong size in model file");
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Legacy-ggml model file (the format reference vit_model_load parses, vit.cpp:308-712; written by convert-pth-to-ggml.py:105-158):
+//   int32 magic 0x67676d6c ("ggml", ggml.h:211), 7 x int32 hparams (hidden, layers, heads, classes, patch, img, ftype; vit.cpp:335-341),
+//   int32 n_labels, n x {int32 id, int32 len, bytes} (vit.cpp:356-371), then per tensor {int32 n_dims, int32 name_len, int32 type,
+//   n_dims x int32 ne, name, raw data} (vit.cpp:590-695).  Validation mirrors the reference (magic, known types, sizes); the tensor
+//   inventory and shapes are checked against the hyper-parameters by vitb200_create.  Fills the same GgufModel.
+inline bool parse_legacy_ggml(const char *buf, size_t size, GgufModel &m)
+{
+    size_t off = 0;
+    auto fail = [&](const std::string &why) { m.error = why; return false; };
+    auto rd32 = [&](int32_t &v) { if (off + 4 > size) return false; memcpy(&v, buf + off, 4); off += 4; return true; };
+    int32_t magic = 0;
+    if (!rd32(magic) || (uint32_t)magic != 0x67676d6cu) return fail("bad magic");
+    int32_t hp[7] = {0};
+    for (int i = 0; i < 7; ++i)
+        if (!rd32(hp[i])) return fail("truncated header");
+    m.hidden_size = hp[0]; m.num_hidden_layers = hp[1]; m.num_attention_heads = hp[2]; m.num_classes = hp[3];
+    m.patch_size = hp[4]; m.img_size = hp[5];
+    m.ftype = hp[6] % 1000; // GGML_QNT_VERSION_FACTOR, vit.cpp:343-354
+    m.eps = 1e-6f;
+    int32_t n_labels = 0;
+    if (!rd32(n_labels) || n_labels < 0) return fail("truncated label table");
+    for (int i = 0; i < n_labels; ++i)
+    {
+        int32_t key = 0, len = 0;
+        if (!rd32(key) || !rd32(len) || len < 0 || (size_t)len > size - off) return fail("truncated label table");
+        m.labels[key] = std::string(buf + off, (size_t)len);
+        off += (size_t)len;
+    }
+    while (off < size)
+    {
+        GgufTensor t;
+        int32_t len = 0;
+        if (!rd32(t.n_dims) || !rd32(len) || !rd32(t.type)) return fail("truncated tensor record");
+        if (t.n_dims < 1 || t.n_dims > 4 || len < 0) return fail("corrupt tensor record");
+        int64_t n = 1;
+        for (int i = 0; i < t.n_dims; ++i)
+        {
+            int32_t d = 0;
+            if (!rd32(d) || d < 1) return fail("corrupt tensor dims");
+            t.ne[i] = d;
+            if (n > (int64_t)(1ull << 40) / d) return fail("corrupt tensor dims (too many elements)");
+            n *= d;
+        }
+        if ((size_t)len > size - off) return fail("truncated tensor name");
+        t.name.assign(buf + off, (size_t)len);
+        off += (size_t)len;
+        if (t.type == 30) return fail("unknown ftype 30 in model file (tensor '" + t.name + "')"); // BF16 exists in GGUF containers only
+        t.nbytes = gguf_type_bytes(t.type, n, t.ne[0]); // vit.cpp:645-678
+        if (t.nbytes == 0)
+            return fail(t.type == 0 || t.type == 1 || t.type == 2 || t.type == 3 || t.type == 6 || t.type == 7 || t.type == 8
+                            ? "tensor '" + t.name + "': quantised rows must be a multiple of 32"
+                            : "unknown ftype " + std::to_string(t.type) + " in model file (tensor '" + t.name + "')");
+        if (t.nbytes > size - off) return fail("tensor '" + t.name + "' has wrong size in model file");
+        t.offset = off;
+        off += t.nbytes;
+        m.tensors.push_back(t);
     }
     return true;
 }
