@@ -33,14 +33,17 @@ typedef struct vitb200_hparams
     int32_t num_classes;
     int32_t patch_size;
     int32_t img_size;
-    int32_t ftype; /* 0 f32, 1 f16, 8 q8_0 (reference vit.cpp:385-414).  f16 is the native path; q8_0 and f32 weights are
-                    * converted to f16 once at upload; other quant formats are rejected */
+    int32_t ftype; /* the model file's ftype (reference vit.cpp:385-414): 0 f32, 1 f16, 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0.
+                    * Informational: what counts is each tensor's own `type`.  f16 is the native path; every other format the
+                    * reference loader accepts is converted to f16 once at upload */
     float eps;     /* layer-norm epsilon, 1e-6 in the reference (vit.h:29) */
 } vitb200_hparams;
 
 /* One host tensor, as found in vit_model::tensors (reference vit.h:88, names at vit.cpp:518-579).
- * `type` uses ggml's type ids for the formats the loader accepts: 0 = F32, 1 = F16, 8 = Q8_0.
- * `ne` is ggml order (ne[0] fastest). */
+ * `type` uses ggml's type ids for the formats the loader accepts: 0 = F32, 1 = F16, 2 = Q4_0, 3 = Q4_1, 6 = Q5_0, 7 = Q5_1,
+ * 8 = Q8_0 (block layouts ggml-quants.h:11-47), plus 30 = BF16 for GGUF containers.  `ne` is ggml order (ne[0] fastest); entries
+ * at index >= n_dims are ignored (treated as 1).  Shapes are checked against the reference's declarations (vit.cpp:510-574) and
+ * names must be unique. */
 typedef struct vitb200_tensor
 {
     const char *name;
@@ -154,8 +157,8 @@ int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, flo
                           const vitb200_taps *taps);
 
 /* Stand-alone run of the tcgen05 GEMM kernel: out[M][N] = epilogue(A[M][K] (f16 bits) x W[N][K]^T (f16 bits)).
- * epilogue: 0 bias->f16, 1 bias+gelu->f16, 2 bias+resid->f32, 4 bias->f32.  out is float32[M][N] on the host
- * (f16 results widened).  resid may be NULL unless epilogue == 2. */
+ * epilogue: 0 bias->f16, 1 bias+gelu->f16, 2 bias+resid->f32, 4 bias->f32, 6 bias->split precision (hi = f16(x), lo = f16(x - hi);
+ * `out` receives hi + lo).  out is float32[M][N] on the host (f16 results widened).  resid may be NULL unless epilogue == 2. */
 int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W,
                       const float *bias, const float *resid, float *out);
 
@@ -164,6 +167,11 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
  * kernel: 0 = the engine's choice for N, 1 = mma.sync two-pass, 2 = tcgen05 single block (N <= 224), 3 = tcgen05 two sweeps
  * (224 < N <= 640). */
 int vitb200_test_attention(int device, int kernel, int B, int N, int H, const uint16_t *qkv, float *out);
+
+/* The tcgen05 single-block attention kernel (N <= 224) on split-precision operands, the way the engine runs it: every q, k, v value is
+ * the sum of two f16 numbers, qkv_hi + qkv_lo (what the qkv GEMM's hi-lo epilogue leaves behind: hi = f16(x), lo = f16(x - hi)), so
+ * the f16 tensor cores reproduce the reference's f32-operand attention mat-muls (vit.cpp:848,858). */
+int vitb200_test_attention_hilo(int device, int B, int N, int H, const uint16_t *qkv_hi, const uint16_t *qkv_lo, float *out);
 
 /* Host-only: the upload-time weight conversion of one quantised tensor, `n_blocks` ggml blocks of 32 weights
  * (type = ggml_type / file ftype: 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0; ggml-quants.h:11-47) -> f16 bits, exactly what

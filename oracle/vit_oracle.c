@@ -93,12 +93,24 @@ static inline float reduce_4x8(const float *s) {
  * disassembly of the reference build and pinned bit-for-bit by tests/test_oracle.py). */
 /* Experiment knob (tests/bench never set it): 0 = the reference's arithmetic (default, bit-exact);
  * 1 = same rounding points but dot products accumulated in double ("any other correct implementation");
- * 2 = 1 + q,k,v rounded to f16 before attention; 3 = 1 + only v rounded to f16.  Used to measure the parity
- * noise floor between non-bit-identical implementations. */
+ * 2 = 1 + q,k,v rounded to f16 before attention; 3 = 1 + only v rounded to f16; 4 = 1 + only q,k rounded to f16;
+ * 5 = 1 + only q rounded; 6 = 1 + only k rounded; 7 = 1 + q,k,v replaced by hi + lo with hi = f16(x), lo = f16(x - hi) (what a
+ * split-precision tensor-core attention sees); 8 = reference rounding points with every dot product accumulated in f32 in blocks
+ * of 16 terms (each block summed exactly, then added to a running f32 sum: a tensor-core-like order).  Used to measure the parity noise floor between non-bit-identical
+ * implementations and which attention operand's precision matters. */
 static int g_variant = 0;
 void vo_set_variant(int v) { g_variant = v; }
 
 static float dot_ggml(int n, const float *x, const float *y, int dbl_tail) {
+    if (g_variant == 8) {
+        float acc = 0.0f;
+        for (int i = 0; i < n; i += 16) {
+            double blk = 0.0;
+            for (int j = i; j < n && j < i + 16; ++j) blk += (double)x[j] * (double)y[j];
+            acc = (float)((double)acc + blk);
+        }
+        return acc;
+    }
     if (g_variant) {
         double acc = 0.0;
         for (int i = 0; i < n; ++i) acc += (double)x[i] * (double)y[i];
@@ -410,7 +422,12 @@ int vo_forward(void *mv, const float *img_hwc, float *logits_out, float *probs_o
         if (tap && taps->ln1) memcpy(taps->ln1, cur, (size_t)N * D * sizeof(float));
         linear(&L->qkv, L->qkv_b, cur, N, qkv);                                 /* vit.cpp:820-821 */
         if (g_variant == 2) for (size_t i = 0; i < (size_t)N * 3 * D; ++i) qkv[i] = round_f16(qkv[i]);
-        if (g_variant == 3) for (int t = 0; t < N; ++t) for (int d = 2 * D; d < 3 * D; ++d) qkv[(size_t)t * 3 * D + d] = round_f16(qkv[(size_t)t * 3 * D + d]);
+        if (g_variant == 7) for (size_t i = 0; i < (size_t)N * 3 * D; ++i) { const float hi = round_f16(qkv[i]); qkv[i] = hi + round_f16(qkv[i] - hi); }
+        if (g_variant >= 3 && g_variant <= 6) {
+            const int c0 = g_variant == 3 ? 2 * D : (g_variant == 6 ? D : 0);
+            const int c1 = g_variant == 3 ? 3 * D : (g_variant == 5 ? D : 2 * D);
+            for (int t = 0; t < N; ++t) for (int d = c0; d < c1; ++d) qkv[(size_t)t * 3 * D + d] = round_f16(qkv[(size_t)t * 3 * D + d]);
+        }
         if (tap && taps->qkv) memcpy(taps->qkv, qkv, (size_t)N * 3 * D * sizeof(float));
 
         { att_ctx ac = {qkv, att, N, D, hd}; par_for(H, attention_heads, &ac); }

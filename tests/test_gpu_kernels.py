@@ -50,6 +50,25 @@ def test_gemm_against_numpy(M, N, K, epi):
         assert (out != ref).mean() < 0.02
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 576, 192), (197 * 3, 2304, 768), (129, 384, 192)])
+def test_gemm_split_precision_epilogue(M, N, K):
+    """EPI_BIAS_F16_HILO (the qkv GEMM in front of the tcgen05 attention): hi = f16(x), lo = f16(x - hi); hi + lo must carry the
+    f32 result to ~2^-21 relative (2^-24 absolute once lo is subnormal), i.e. only fp32 accumulation-order noise remains."""
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float16)
+    W = (rng.standard_normal((N, K)) * 0.05).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float32)
+    out = eng.test_gemm(M, N, K, 6, A, W, bias)
+    ref = (A.astype(np.float64) @ W.astype(np.float64).T + bias).astype(np.float32)
+    hi, lo = eng.split_hi_lo(ref)
+    want = hi.astype(np.float32) + lo.astype(np.float32)
+    assert np.abs(want - ref).max() <= 2.0 ** -21 * np.abs(ref).max()      # the representation itself
+    np.testing.assert_allclose(out, ref, rtol=0, atol=2e-5 * max(1.0, np.abs(ref).max()) * 0.1 + 2.0 ** -20 * np.abs(ref).max())
+    # and the hi part alone is exactly what the plain f16 epilogue writes
+    plain = eng.test_gemm(M, N, K, 0, A, W, bias)
+    assert (np.abs(out - plain) <= 2.0 ** -11 * np.abs(plain) + 2.0 ** -24).all()
+
+
 def test_gemm_linearity_at_full_size():
     """Size-independent property at the BASELINE batch size (M = 256*197 = 50432): GEMM(A, W1 + W2) with zero bias equals
     GEMM(A, W1) + GEMM(A, W2) up to fp32 rounding, for exactly representable small-integer operands it is EXACT."""
@@ -80,6 +99,40 @@ def _attention_ref(qkv16, B, N, H):
     e = np.exp(z).astype(np.float16).astype(np.float64)
     o = np.einsum("bhqk,bhkd->bhqd", e, v) / e.sum(-1, keepdims=True)
     return o.transpose(0, 2, 1, 3).reshape(B * N, D)
+
+
+def _attention_ref_f32(qkv32, B, N, H):
+    """The same on f32 q, k, v (what the reference's attention mat-muls see, vit.cpp:848,858)."""
+    D = H * 64
+    x = qkv32.astype(np.float64).reshape(B, N, 3, H, 64)
+    q, k, v = x[:, :, 0].transpose(0, 2, 1, 3), x[:, :, 1].transpose(0, 2, 1, 3), x[:, :, 2].transpose(0, 2, 1, 3)
+    s = np.einsum("bhqd,bhkd->bhqk", q, k).astype(np.float32) * np.float32(0.125)
+    z = (s - s.max(-1, keepdims=True)).astype(np.float16).astype(np.float64)
+    e = np.exp(z).astype(np.float16).astype(np.float64)
+    o = np.einsum("bhqk,bhkd->bhqd", e, v) / e.sum(-1, keepdims=True)
+    return o.transpose(0, 2, 1, 3).reshape(B * N, D), s
+
+
+@pytest.mark.parametrize("B,N,H", [(3, 17, 2), (2, 197, 3), (1, 224, 1), (40, 197, 12), (2, 50, 1)])
+def test_attention_split_precision_against_f32_operand_reference(B, N, H):
+    """attention_tc_kernel with hi + lo operands must follow the f32-operand restatement, not the f16-operand one: a score error of
+    2^-12 relative (what rounding q or k to f16 costs) moves x - max across f16 rounding boundaries; with split operands the only
+    differences left are f32 accumulation order + the f16 roundings the reference makes too.  The last case keeps every CTA looping
+    over several (image, head) problems (single-buffered operand groups: empty/full barrier parities)."""
+    rng = np.random.default_rng(N * 7 + H)
+    qkv = rng.normal(0.0, 1.0, (B * N, 3 * H * 64)).astype(np.float32)
+    qkv[:, : H * 64] *= 1.5
+    hi, lo = eng.split_hi_lo(qkv)
+    q22 = hi.astype(np.float32) + lo.astype(np.float32)   # the 22-bit values the kernel actually sees
+    out = eng.test_attention_hilo(qkv, B, N, H)
+    ref, _ = _attention_ref_f32(q22, B, N, H)
+    ref16, _ = _attention_ref_f32(hi.astype(np.float32), B, N, H)
+    assert np.isfinite(out).all()
+    err = np.abs(out - ref)
+    tol = 2.0 ** -10 * np.abs(ref) + 2e-3 * np.abs(ref).max()
+    assert (err <= tol).all(), (err.max(), np.abs(ref).max(), np.unravel_index(err.argmax(), err.shape))
+    # closer to the f32-operand result than to the f16-operand one (mean absolute deviation over all outputs)
+    assert np.abs(out - ref).mean() < 0.6 * np.abs(out - ref16).mean(), (np.abs(out - ref).mean(), np.abs(out - ref16).mean())
 
 
 ATTN_CASES = [  # (B, N, H, kernel)

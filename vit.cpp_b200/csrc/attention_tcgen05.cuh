@@ -3,6 +3,12 @@
 // Replaces the reference's 16 reshape/permute/CONT nodes + mul_mat(K,Q) + scale + soft_max_inplace + mul_mat(V,P) + head
 // merge (reference vit.cpp:826-866; CPU kernels ggml.c:1163-1198 (f32 dot), 10498-10567 (soft-max)).
 //
+// Precision: the reference feeds F32 q, k, v to both attention mat-muls (vit.cpp:848,858).  The qkv GEMM therefore leaves every
+// value as TWO f16 numbers, hi = f16(x) and lo = f16(x - hi) (hi + lo carries ~22 significant bits), and the tensor cores run
+//   S = Ql Kh^T + Qh Kl^T + Qh Kh^T   (the Ql Kl^T term is below 2^-22 relative)        O = P Vl + P Vh   (P is exactly f16)
+// with f32 accumulation in TMEM: rounding q, k or v to f16 alone costs ~17 % of the logit-parity budget (CPU experiment,
+// DESIGN.md section 4).  p.hilo = 0 (lo tensors absent) runs the single-term products.
+//
 //   S = Q K^T      tcgen05.mma SS: A = Q tile (128 x 64, K-major, TMA SWIZZLE_128B), B = K (NKP x 64, K-major), D in TMEM
 //   P = softmax    thread = query row = TMEM lane: TRUE row max (2 TMEM passes), e = f16(exp(f16(s/8 - max))) exactly the
 //                  reference's table semantics (ggml.c:10547-10549), un-normalised P written back into the S columns as packed
@@ -11,8 +17,11 @@
 //                  staged in shared memory (SWIZZLE_128B) and written with one TMA store per warp
 //
 // Q, K, V are read straight out of the [tokens][3*D] QKV buffer by TMA (column offset h*64 / D + h*64 / 2D + h*64): no
-// split / transpose copies.  Persistent CTAs (1 per SM), 10 warps: warp 0 TMA producer (2-stage ring over problems),
-// warp 1 MMA issuer, warps 2-5 / 6-9 soft-max + epilogue warpgroups for query tile 0 / 1 (rows 0-127 / 128-255).
+// split / transpose copies.  Persistent CTAs (1 per SM), 10 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9
+// soft-max + epilogue warpgroups for query tile 0 / 1 (rows 0-127 / 128-255).  Shared memory holds ONE problem's operands
+// (hi + lo: up to 176 KB) with a full/empty mbarrier pair per operand group -- Q tile 0, Q tile 1, K, V -- so each group of the
+// next problem is re-loaded as soon as the last MMA reading it has retired (Q/K right after the scores, V after P V), i.e.
+// a whole problem period before it is needed.
 // Supports N <= 224 tokens (keys padded to NKP = ceil16(N) <= 224: S0 at TMEM cols [0,224), S1 at [224,448), O at [448,512)).
 #pragma once
 #include "kernels.cuh"
@@ -27,6 +36,7 @@ struct AttnTcParams
     int n_mtiles; // 1 or 2 query tiles of 128 rows
     int kv_bytes; // NKP * 128 rounded up to 1024
     float scale;  // 1/sqrt(64)
+    int hilo;     // 1: split-precision operands (lo tensors present); 0: hi only
     long long *trace; // dev only (VITB200_ATTN_TRACE): clock64 stamps of CTA 0, [problem < 16][slot < 32]; NULL in production
 };
 
@@ -44,48 +54,73 @@ __device__ __forceinline__ uint32_t att_exp_pair(float x0, float x1, float &lsum
     ptx::add_f32_f16(lsum, __half_as_ushort(__high2half(e)));
     return *reinterpret_cast<const uint32_t *>(&e);
 }
+// The same from two raw scores: x = s * scale - max as ONE packed FFMA2 and the log2(e) multiply as one FMUL2 (Blackwell packed
+// FP32: half the issue slots of the scalar forms; each lane is a separately rounded IEEE operation, results are bit-identical).
+__device__ __forceinline__ uint32_t att_exp_pair_raw(uint32_t s0, uint32_t s1, uint64_t scale2, uint64_t nmax2, float &lsum)
+{
+    float x0, x1;
+    ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(s0), __uint_as_float(s1)), scale2, nmax2), x0, x1);
+    const float2 xr = __half22float2(__floats2half2_rn(x0, x1));
+    float y0, y1;
+    ptx::unpack_f32x2(ptx::mul_f32x2(ptx::pack_f32x2(xr.x, xr.y), ptx::pack_f32x2(1.4426950408889634f, 1.4426950408889634f)), y0, y1);
+    const __half2 e = __floats2half2_rn(ptx::ex2_approx(y0), ptx::ex2_approx(y1));
+    ptx::add_f32_f16(lsum, __half_as_ushort(__low2half(e)));
+    ptx::add_f32_f16(lsum, __half_as_ushort(__high2half(e)));
+    return *reinterpret_cast<const uint32_t *>(&e);
+}
+
+// dynamic shared memory of attention_tc_kernel: alignment slack + 4 Q tiles (hi/lo x 2 query tiles) + K, V (hi/lo) + 8 store boxes + barriers
+__host__ __device__ inline int attention_tc_smem_bytes(int kv_bytes) { return 1024 + 4 * 16384 + 4 * kv_bytes + 8 * 4096 + 256; }
 
 __global__ void __launch_bounds__(ATT_TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmQl, const __grid_constant__ CUtensorMap tmKVl,
                     const __grid_constant__ CUtensorMap tmO, const AttnTcParams p)
 {
     extern __shared__ uint8_t att_tc_smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(att_tc_smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = att_tc_smem_raw + (smem_base - ptx::smem_u32(att_tc_smem_raw));
-    const uint32_t stage_bytes = 2 * 16384 + 2 * p.kv_bytes;
-    auto sQ = [&](int st, int t) { return smem_base + st * stage_bytes + t * 16384; };
-    auto sK = [&](int st) { return smem_base + st * stage_bytes + 2 * 16384; };
-    auto sV = [&](int st) { return smem_base + st * stage_bytes + 2 * 16384 + p.kv_bytes; };
-    const uint32_t stage_out = smem_base + 2 * stage_bytes; // 8 x 4 KB: one 32-row x 128-B SWIZZLE_128B store box per soft-max warp
+    // operand layout (one problem): Qh tile 0 | Qh tile 1 | Ql tile 0 | Ql tile 1 | Kh | Kl | Vh | Vl   (hl = 0 hi, 1 lo)
+    auto sQ = [&](int hl, int t) { return smem_base + (uint32_t)(hl * 2 + t) * 16384u; };
+    auto sK = [&](int hl) { return smem_base + 4u * 16384u + (uint32_t)hl * (uint32_t)p.kv_bytes; };
+    auto sV = [&](int hl) { return smem_base + 4u * 16384u + (uint32_t)(2 + hl) * (uint32_t)p.kv_bytes; };
+    const uint32_t stage_out = smem_base + 4u * 16384u + 4u * (uint32_t)p.kv_bytes; // 8 x 4 KB: one 32-row x 128-B SWIZZLE_128B store box per soft-max warp
     const uint32_t bars = stage_out + 8 * 4096;
-    // barriers: load_full[2], load_empty[2], s_full[2], p_ready[2], o_full[2], o_empty[2], tmem ptr
-    auto load_full = [&](int s) { return bars + 8u * s; };
-    auto load_empty = [&](int s) { return bars + 8u * (2 + s); };
-    auto s_full = [&](int t) { return bars + 8u * (4 + t); };
-    auto p_ready = [&](int t) { return bars + 8u * (6 + t); };
-    auto o_full = [&](int t) { return bars + 8u * (8 + t); };
-    auto o_empty = [&](int t) { return bars + 8u * (10 + t); };
-    const uint32_t tmem_ptr_addr = bars + 8u * 12;
-    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + 2 * stage_bytes + 8 * 4096 + 8 * 12);
+    // barriers: q_full[2], q_empty[2], k_full, k_empty, v_full, v_empty, s_full[2], p_ready[2], o_full[2], o_empty[2], tmem ptr
+    auto q_full = [&](int t) { return bars + 8u * t; };
+    auto q_empty = [&](int t) { return bars + 8u * (2 + t); };
+    const uint32_t k_full = bars + 8u * 4, k_empty = bars + 8u * 5, v_full = bars + 8u * 6, v_empty = bars + 8u * 7;
+    auto s_full = [&](int t) { return bars + 8u * (8 + t); };
+    auto p_ready = [&](int t) { return bars + 8u * (10 + t); };
+    auto o_full = [&](int t) { return bars + 8u * (12 + t); };
+    auto o_empty = [&](int t) { return bars + 8u * (14 + t); };
+    const uint32_t tmem_ptr_addr = bars + 8u * 16;
+    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem + 4 * 16384 + 4 * p.kv_bytes + 8 * 4096 + 8 * 16);
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool hilo = p.hilo != 0;
     if (warp_idx == 0 && lane == 0)
     {
         ptx::prefetch_tensormap(&tmQ);
         ptx::prefetch_tensormap(&tmKV);
         ptx::prefetch_tensormap(&tmO);
+        if (hilo) { ptx::prefetch_tensormap(&tmQl); ptx::prefetch_tensormap(&tmKVl); }
     }
     if (warp_idx == 1 && lane == 0)
     {
         for (int i = 0; i < 2; ++i)
         {
-            ptx::mbar_init(load_full(i), 1);
-            ptx::mbar_init(load_empty(i), 1);
+            ptx::mbar_init(q_full(i), 1);
+            ptx::mbar_init(q_empty(i), 1);
             ptx::mbar_init(s_full(i), 1);
             ptx::mbar_init(p_ready(i), 4);
             ptx::mbar_init(o_full(i), 1);
             ptx::mbar_init(o_empty(i), 4);
         }
+        ptx::mbar_init(k_full, 1);
+        ptx::mbar_init(k_empty, 1);
+        ptx::mbar_init(v_full, 1);
+        ptx::mbar_init(v_empty, 1);
         ptx::fence_barrier_init();
     }
     if (warp_idx == 2)
@@ -104,21 +139,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp_idx == 0)
     {
         // ===================== TMA producer =====================
+        // Per problem: K, Q tile 0, Q tile 1, then V -- each group as soon as its previous contents have been consumed (the
+        // *_empty barriers are tcgen05.commit arrivals behind the last MMA that read the group).
         if (lane == 0)
         {
+            const uint32_t kv_tx = (uint32_t)(p.NKP * 128) * (hilo ? 2u : 1u), q_tx = 16384u * (hilo ? 2u : 1u);
+            // L2 prefetch of every operand tile of one problem: shared memory holds a single problem, so the real loads can only be
+            // issued late (when the previous problem's MMAs retire); prefetching a problem ahead moves the HBM latency and the
+            // bandwidth burst off that critical window -- the loads then come out of L2.
+            auto prefetch = [&](int prob) {
+                const int b = prob / p.H, h = prob - b * p.H, row0 = b * p.N;
+                for (int hl = 0; hl < (hilo ? 2 : 1); ++hl)
+                {
+                    const CUtensorMap *mkv = hl ? &tmKVl : &tmKV, *mq = hl ? &tmQl : &tmQ;
+                    ptx::tma_prefetch_2d(mkv, p.D + h * 64, row0);
+                    for (int t = 0; t < p.n_mtiles; ++t) ptx::tma_prefetch_2d(mq, h * 64, row0 + t * 128);
+                    ptx::tma_prefetch_2d(mkv, 2 * p.D + h * 64, row0);
+                }
+            };
             int i = 0;
             for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
             {
-                const int st = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
+                const uint32_t ph = (uint32_t)(i & 1);
                 const int b = prob / p.H, h = prob - b * p.H;
                 const int row0 = b * p.N;
-                ptx::mbar_wait(load_empty(st), ph ^ 1);
-                ptx::mbar_arrive_expect_tx(load_full(st), (uint32_t)(p.n_mtiles * 16384 + 2 * p.NKP * 128));
-                ptx::tma_load_2d(sK(st), &tmKV, load_full(st), p.D + h * 64, row0);
-                ptx::tma_load_2d(sQ(st, 0), &tmQ, load_full(st), h * 64, row0);
-                if (p.n_mtiles == 2) ptx::tma_load_2d(sQ(st, 1), &tmQ, load_full(st), h * 64, row0 + 128);
-                ptx::tma_load_2d(sV(st), &tmKV, load_full(st), 2 * p.D + h * 64, row0);
+                ptx::mbar_wait(k_empty, ph ^ 1);
+                ptx::mbar_arrive_expect_tx(k_full, kv_tx);
+                ptx::tma_load_2d(sK(0), &tmKV, k_full, p.D + h * 64, row0);
+                if (hilo) ptx::tma_load_2d(sK(1), &tmKVl, k_full, p.D + h * 64, row0);
+                for (int t = 0; t < p.n_mtiles; ++t)
+                {
+                    ptx::mbar_wait(q_empty(t), ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(q_full(t), q_tx);
+                    ptx::tma_load_2d(sQ(0, t), &tmQ, q_full(t), h * 64, row0 + t * 128);
+                    if (hilo) ptx::tma_load_2d(sQ(1, t), &tmQl, q_full(t), h * 64, row0 + t * 128);
+                }
+                // K/Q of this problem are on their way; now ask L2 for everything the NEXT problem will need
+                if (prob + (int)gridDim.x < p.n_problems) prefetch(prob + (int)gridDim.x);
+                ptx::mbar_wait(v_empty, ph ^ 1);
+                ptx::mbar_arrive_expect_tx(v_full, kv_tx);
+                ptx::tma_load_2d(sV(0), &tmKV, v_full, 2 * p.D + h * 64, row0);
+                if (hilo) ptx::tma_load_2d(sV(1), &tmKVl, v_full, 2 * p.D + h * 64, row0);
             }
         }
         __syncwarp();
@@ -130,59 +191,63 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint32_t idesc_s = ptx::umma_idesc_f16(128, p.NKP, 0, 0, 0, 0);
             const uint32_t idesc_o = ptx::umma_idesc_f16(128, 64, 0, 0, 0, /*B (V) is MN-major*/ 1);
             const int ksteps = p.NKP / 16;
-            // S_t = Q_t K^T of one problem (4 MMAs, K = 64)
-            auto issue_s = [&](int st, int t) {
-                const uint64_t kdesc = ptx::umma_desc_kmajor_sw128(sK(st));
-                const uint64_t qdesc = ptx::umma_desc_kmajor_sw128(sQ(st, t));
+            const int last_t = p.n_mtiles - 1;
+            // S_t = Q_t K^T of problem `j` (its operands must have landed): small cross terms first, then the hi x hi product
+            auto issue_s = [&](int t, int j) {
+                if (t == 0) ptx::mbar_wait(k_full, (uint32_t)(j & 1));
+                ptx::mbar_wait(q_full(t), (uint32_t)(j & 1));
+                ptx::tcgen05_fence_after();
+                const uint64_t kh = ptx::umma_desc_kmajor_sw128(sK(0)), kl = ptx::umma_desc_kmajor_sw128(sK(1));
+                const uint64_t qh = ptx::umma_desc_kmajor_sw128(sQ(0, t)), ql = ptx::umma_desc_kmajor_sw128(sQ(1, t));
                 if (ptx::elect_one())
                 {
+                    if (hilo)
+                    {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ptx::tcgen05_mma_f16(tmem_base + scol[t], qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0);
+                        for (int k = 0; k < 4; ++k) ptx::tcgen05_mma_f16(tmem_base + scol[t], ql + 2 * k, kh + 2 * k, idesc_s, k > 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ptx::tcgen05_mma_f16(tmem_base + scol[t], qh + 2 * k, kl + 2 * k, idesc_s, 1);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::tcgen05_mma_f16(tmem_base + scol[t], qh + 2 * k, kh + 2 * k, idesc_s, (hilo || k > 0) ? 1 : 0);
                     ptx::tcgen05_commit(s_full(t));
+                    ptx::tcgen05_commit(q_empty(t));              // Q tile t may be overwritten once these MMAs retire
+                    if (t == last_t) ptx::tcgen05_commit(k_empty); // ... and K after the last tile's scores
                 }
                 __syncwarp();
             };
             int i = 0;
             const int first = blockIdx.x;
             if (first < p.n_problems)
-            {
-                ptx::mbar_wait(load_full(0), 0);
-                ptx::tcgen05_fence_after();
-                for (int t = 0; t < p.n_mtiles; ++t) issue_s(0, t);
-            }
+                for (int t = 0; t < p.n_mtiles; ++t) issue_s(t, 0);
             for (int prob = first; prob < p.n_problems; prob += gridDim.x, ++i)
             {
-                const int st = i & 1;
                 const bool has_next = prob + (int)gridDim.x < p.n_problems;
-                const uint64_t vdesc = ptx::umma_desc_mnmajor_sw128(sV(st), (uint32_t)p.kv_bytes);
+                const uint64_t vh = ptx::umma_desc_mnmajor_sw128(sV(0), (uint32_t)p.kv_bytes);
+                const uint64_t vl = ptx::umma_desc_mnmajor_sw128(sV(1), (uint32_t)p.kv_bytes);
                 for (int t = 0; t < p.n_mtiles; ++t)
                 {
                     ptx::mbar_wait(p_ready(t), i & 1); // P_t is in TMEM (and the soft-max warps are done with S_t)
                     // the single O accumulator must have been drained by its previous user
-                    if (t == 0) { if (i > 0) ptx::mbar_wait(o_empty(p.n_mtiles - 1), (i - 1) & 1); }
+                    if (t == 0) { if (i > 0) ptx::mbar_wait(o_empty(last_t), (i - 1) & 1); }
                     else ptx::mbar_wait(o_empty(0), i & 1);
+                    if (t == 0) ptx::mbar_wait(v_full, (uint32_t)(i & 1));
                     ptx::tcgen05_fence_after();
                     if (ptx::elect_one())
                     {
-                        for (int j = 0; j < ksteps; ++j) // 16 keys per step: 8 TMEM columns of packed f16, 16 rows (2048 B) of V
-                            ptx::tcgen05_mma_f16_ts(tmem_base + ATT_TC_OCOL, tmem_base + scol[t] + 8 * j, vdesc + (uint64_t)(j * 128), idesc_o, j > 0);
+                        // 16 keys per step: 8 TMEM columns of packed f16, 16 rows (2048 B) of V; O = P Vl + P Vh
+                        if (hilo)
+                            for (int j = 0; j < ksteps; ++j)
+                                ptx::tcgen05_mma_f16_ts(tmem_base + ATT_TC_OCOL, tmem_base + scol[t] + 8 * j, vl + (uint64_t)(j * 128), idesc_o, j > 0);
+                        for (int j = 0; j < ksteps; ++j)
+                            ptx::tcgen05_mma_f16_ts(tmem_base + ATT_TC_OCOL, tmem_base + scol[t] + 8 * j, vh + (uint64_t)(j * 128), idesc_o, (hilo || j > 0) ? 1 : 0);
                         ptx::tcgen05_commit(o_full(t));
-                        if (t == p.n_mtiles - 1) ptx::tcgen05_commit(load_empty(st)); // all MMAs reading this smem stage have retired
+                        if (t == last_t) ptx::tcgen05_commit(v_empty); // all MMAs reading V have retired
                     }
                     __syncwarp();
-                    // S_t of the NEXT problem (other smem stage) goes into the pipe right behind P_t V: the in-order tensor
-                    // pipe runs it after P_t V has consumed the aliased P_t columns, so tile t's warpgroup finds its next
-                    // scores ready as soon as it has drained O
-                    if (has_next)
-                    {
-                        if (t == 0)
-                        {
-                            ptx::mbar_wait(load_full(st ^ 1), ((i + 1) >> 1) & 1);
-                            ptx::tcgen05_fence_after();
-                        }
-                        issue_s(st ^ 1, t);
-                    }
+                    // S_t of the NEXT problem goes into the pipe right behind P_t V: the in-order tensor pipe runs it after P_t V has
+                    // consumed the aliased P_t columns, so tile t's warpgroup finds its next scores ready as soon as it has drained O
+                    if (has_next) issue_s(t, i + 1);
                 }
             }
         }
@@ -200,6 +265,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + ATT_TC_OCOL;
             const int n32 = p.NKP >> 5;
             const bool tail16 = (p.NKP & 16) != 0;
+            const uint64_t scale2 = ptx::pack_f32x2(p.scale, p.scale);
             int i = 0;
             for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
             {
@@ -216,6 +282,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     {
                         float ma = -INFINITY, mb = -INFINITY;
                         int c = 0;
+#pragma unroll 1
                         for (; c + 2 <= (p.N >> 5); c += 2) // two mask-free chunks per iteration
                         {
                             uint32_t va[32], vb[32];
@@ -226,6 +293,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             for (int j = 0; j < 32; ++j) { ma = fmaxf(ma, __uint_as_float(va[j])); mb = fmaxf(mb, __uint_as_float(vb[j])); }
                         }
                         mx = fmaxf(ma, mb);
+#pragma unroll 1
                         for (; c < n32; ++c)
                         {
                             uint32_t v[32];
@@ -247,12 +315,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                     if (q == 0) ATT_TRACE(8 * t + 2);
                     const float mxs = mx * p.scale; // ggml_scale_inplace (vit.cpp:851-854); exact, scale = 1/8
+                    const uint64_t nmax2 = ptx::pack_f32x2(-mxs, -mxs);
                     // ---- pass 2: P = f16(exp(f16(s*scale - max))) -> packed f16 into the S columns, l = sum P.
                     // Full (mask-free) chunks go two at a time with four independent partial sums so one warp keeps the
                     // MUFU / conversion latencies overlapped; the chunk(s) straddling N take the masked path.
                     const int n_full = p.N >> 5; // chunks with all 32 keys valid
                     float l0 = 0.f, l1 = 0.f, l2s = 0.f, l3 = 0.f;
                     int c = 0;
+#pragma unroll 1 // (ptxas otherwise unrolls x4 with three peeled copies: 213 KB of SASS, the live part no longer fits the instruction cache)
                     for (; c + 2 <= n_full; c += 2)
                     {
                         uint32_t va[32], vb[32], pa[16], pb[16];
@@ -262,15 +332,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 16; j += 2)
                         {
-                            pa[j] = att_exp_pair(__fmaf_rn(__uint_as_float(va[2 * j]), p.scale, -mxs), __fmaf_rn(__uint_as_float(va[2 * j + 1]), p.scale, -mxs), l0);
-                            pb[j] = att_exp_pair(__fmaf_rn(__uint_as_float(vb[2 * j]), p.scale, -mxs), __fmaf_rn(__uint_as_float(vb[2 * j + 1]), p.scale, -mxs), l1);
-                            pa[j + 1] = att_exp_pair(__fmaf_rn(__uint_as_float(va[2 * j + 2]), p.scale, -mxs), __fmaf_rn(__uint_as_float(va[2 * j + 3]), p.scale, -mxs), l2s);
-                            pb[j + 1] = att_exp_pair(__fmaf_rn(__uint_as_float(vb[2 * j + 2]), p.scale, -mxs), __fmaf_rn(__uint_as_float(vb[2 * j + 3]), p.scale, -mxs), l3);
+                            pa[j] = att_exp_pair_raw(va[2 * j], va[2 * j + 1], scale2, nmax2, l0);
+                            pb[j] = att_exp_pair_raw(vb[2 * j], vb[2 * j + 1], scale2, nmax2, l1);
+                            pa[j + 1] = att_exp_pair_raw(va[2 * j + 2], va[2 * j + 3], scale2, nmax2, l2s);
+                            pb[j + 1] = att_exp_pair_raw(vb[2 * j + 2], vb[2 * j + 3], scale2, nmax2, l3);
                         }
                         ptx::tcgen05_st_32x32b_x16(t_s + c * 16, pa);
                         ptx::tcgen05_st_32x32b_x16(t_s + c * 16 + 16, pb);
                     }
                     lsum = (l0 + l1) + (l2s + l3);
+#pragma unroll 1
                     for (; c < n32; ++c)
                     {
                         uint32_t v[32], pk[16];

@@ -141,6 +141,8 @@ struct vitb200_engine
     vitb200_hparams hp;
     int device = 0, max_batch = 0, num_sms = 148;
     int N = 0, NP = 0, G = 0, KP = 0, KPp = 0;
+    int Cp = 0;           // num_classes rounded up to a multiple of 4: pitch of the internal logits rows (128-bit epilogue stores)
+    float *d_sm_scratch = nullptr; // soft-max working rows in global memory, only when num_classes floats exceed shared memory
     int C = 3;            // input channels: 3 (vit.cpp) or 1 (ViTSTR extension, vitstr.cpp:713), taken from the patch kernel's shape
     int head_tokens = 1;  // tokens the classifier head reads per image: 1 (token 0, vit.cpp:910) or 25 (vitstr.cpp:864-903)
     cudaStream_t stream = nullptr;
@@ -153,7 +155,11 @@ struct vitb200_engine
     float *d_img = nullptr, *X = nullptr, *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
     int32_t *d_topk_idx = nullptr;
     __half *A16 = nullptr, *QKV16 = nullptr, *H16 = nullptr, *CLS16 = nullptr, *PA = nullptr;
+    __half *QKV16L = nullptr; // lo halves of q, k, v (x - f16(x), as f16): the tcgen05 attention's split-precision operands
+    bool attn_hilo = false;   // qkv GEMM emits hi + lo and attention_tc_kernel runs the 3 + 2 term products (VITB200_ATTN_HILO=0: hi only)
+    CUtensorMap tmQl, tmKVl;
     CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX, tmQ, tmKV, tmAO, tmKV64;
+    std::map<int, CUtensorMap> tmX_batch; // residual-stream map clipped to batch * N rows: TMA neither loads nor stores rows past the batch
     bool attn_tc = false;      // tcgen05 single-block attention (N <= 224)
     bool attn_tc_long = false; // tcgen05 two-sweep attention (224 < N <= 640); anything longer uses the mma.sync two-pass kernel
     int max_k = 16;
@@ -200,8 +206,35 @@ int dev_alloc(vitb200_engine *e, T **p, size_t count)
 const vitb200_tensor *find_tensor(const vitb200_tensor *t, int n, const std::string &name)
 {
     for (int i = 0; i < n; ++i)
-        if (name == t[i].name) return &t[i];
+        if (t[i].name && name == t[i].name) return &t[i];
     return nullptr;
+}
+
+// the reference keeps tensors in a std::map keyed by name (vit.h:88), so a name can only occur once; a caller-built list with a
+// repeated name is rejected instead of silently taking the first
+int check_unique_names(const vitb200_tensor *t, int n)
+{
+    std::map<std::string, int> seen;
+    for (int i = 0; i < n; ++i)
+    {
+        if (!t[i].name || !t[i].data) return fail("tensor %d has a null name or data pointer", i);
+        if (t[i].n_dims < 1 || t[i].n_dims > 4) return fail("tensor '%s' has %d dimensions", t[i].name, t[i].n_dims);
+        if (seen.count(t[i].name)) return fail("duplicate tensor '%s' in model", t[i].name);
+        seen[t[i].name] = i;
+    }
+    return 0;
+}
+
+int64_t dim_of(const vitb200_tensor *t, int i) { return i < t->n_dims ? t->ne[i] : 1; }
+
+// the reference loader's shape check (vit.cpp:633-641): all four ggml extents must match the tensor the model declares
+int check_shape(const vitb200_tensor *x, const std::string &name, int64_t e0, int64_t e1, int64_t e2, int64_t e3)
+{
+    if (dim_of(x, 0) != e0 || dim_of(x, 1) != e1 || dim_of(x, 2) != e2 || dim_of(x, 3) != e3)
+        return fail("tensor '%s' has wrong shape in model file: got [%lld, %lld, %lld, %lld], expected [%lld, %lld, %lld, %lld]", name.c_str(),
+                    (long long)dim_of(x, 0), (long long)dim_of(x, 1), (long long)dim_of(x, 2), (long long)dim_of(x, 3),
+                    (long long)e0, (long long)e1, (long long)e2, (long long)e3);
+    return 0;
 }
 
 int64_t nelem(const vitb200_tensor *t)
@@ -211,13 +244,18 @@ int64_t nelem(const vitb200_tensor *t)
     return n;
 }
 
-int upload_f32(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &name, int64_t expect, float **dst)
+// f32 tensor with the reference's declared extents {e0, e1, e2, e3} (vit.cpp:510-574); `padded` >= the element count allocates a
+// zero-filled tail (the classifier bias when num_classes is not a multiple of 4)
+int upload_f32(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &name, int64_t e0, int64_t e1, int64_t e2, int64_t e3,
+               float **dst, int64_t padded = 0)
 {
     const vitb200_tensor *x = find_tensor(t, n, name);
     if (!x) return fail("missing tensor '%s'", name.c_str());
     if (x->type != 0) return fail("tensor '%s' must be f32 (type %d)", name.c_str(), x->type);
-    if (nelem(x) != expect) return fail("tensor '%s' has wrong size: got %lld, expected %lld", name.c_str(), (long long)nelem(x), (long long)expect);
-    if (dev_alloc(e, dst, (size_t)expect)) return 1;
+    const int64_t expect = e0 * e1 * e2 * e3;
+    if (nelem(x) != expect) return fail("tensor '%s' has wrong size in model file: got %lld, expected %lld", name.c_str(), (long long)nelem(x), (long long)expect);
+    if (check_shape(x, name, e0, e1, e2, e3)) return 1;
+    if (dev_alloc(e, dst, (size_t)(padded > expect ? padded : expect))) return 1;
     CUDA_TRY(cudaMemcpy(*dst, x->data, (size_t)expect * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -287,13 +325,15 @@ void dequant_block(int type, const uint8_t *blk, float *y)
 //   type 0 (F32): rounded once to f16 (the reference keeps f32 weights AND f32 activations, ggml.c:1163-1198).
 //   type 30 (BF16, GGUF containers): widened to f32, then as type 0.
 int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::string &wname, const std::string &bname,
-                  int n_out, int n_in, int ld, Linear *L)
+                  int n_out, int n_in, int ld, Linear *L, int conv_p = 0)
 {
     const vitb200_tensor *w = find_tensor(t, n, wname);
     if (!w) return fail("missing tensor '%s'", wname.c_str());
     if (w->type != 0 && w->type != 1 && w->type != 30 && quant_block_bytes(w->type) == 0)
         return fail("tensor '%s': weight type %d is not supported (f32, f16, bf16, q4_0, q4_1, q5_0, q5_1, q8_0 only)", wname.c_str(), w->type);
-    if (nelem(w) != (int64_t)n_out * n_in) return fail("tensor '%s' has wrong size: got %lld, expected %lld", wname.c_str(), (long long)nelem(w), (long long)n_out * n_in);
+    if (nelem(w) != (int64_t)n_out * n_in) return fail("tensor '%s' has wrong size in model file: got %lld, expected %lld", wname.c_str(), (long long)nelem(w), (long long)n_out * n_in);
+    if (conv_p > 0) { if (check_shape(w, wname, conv_p, conv_p, n_in / (conv_p * conv_p), n_out)) return 1; } // [P, P, C, D], vit.cpp:515
+    else if (check_shape(w, wname, n_in, n_out, 1, 1)) return 1;                                             // [in, out], vit.cpp:531-543
     if (quant_block_bytes(w->type) && n_in % 32 != 0) return fail("tensor '%s': quantised rows must be a multiple of 32", wname.c_str());
     L->n_out = n_out; L->n_in = n_in; L->ld = ld; L->bn = pick_bn(n_out);
     if (dev_alloc(e, &L->w, (size_t)n_out * ld)) return 1;
@@ -338,9 +378,13 @@ int upload_linear(vitb200_engine *e, const vitb200_tensor *t, int n, const std::
         src = conv.data();
     }
     CUDA_TRY(cudaMemcpy2D(L->w, (size_t)ld * 2, src, (size_t)n_in * 2, (size_t)n_in * 2, (size_t)n_out, cudaMemcpyHostToDevice));
-    if (upload_f32(e, t, n, bname, n_out, &L->b)) return 1;
+    // conv bias is declared [1, 1, D] (vit.cpp:516), every other bias [n_out]; the tail up to a multiple of 4 stays zero
+    if (conv_p > 0 ? upload_f32(e, t, n, bname, 1, 1, n_out, 1, &L->b) : upload_f32(e, t, n, bname, n_out, 1, 1, 1, &L->b, (n_out + 3) / 4 * 4)) return 1;
     return make_tmap(&L->tm, L->w, (uint64_t)n_out, (uint64_t)ld, (uint64_t)ld, (uint32_t)(L->bn / e->cta_group));
 }
+
+// dynamic shared memory the soft-max kernel may use for its working row (227 KB per CTA minus its static arrays)
+constexpr size_t kSoftmaxSmemMax = 232448 - 1024;
 
 enum ProfKind { PK_PATCH = 0, PK_QKV, PK_PROJ, PK_FC1, PK_FC2, PK_HEAD, PK_ATTN, PK_LN, PK_COUNT };
 
@@ -393,7 +437,8 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 template <int BN, int EPI, int CG, int DEEPK = 0>
 int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
 {
-    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0>;
+    using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0,
+                        EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_F16_HILO>;
     auto kern = gemm_tcgen05_kernel<BN, EPI, DEEPK, CG>;
     // the opt-in to > 48 KB dynamic shared memory is per device (one engine per device, possibly several per process)
     static bool attr_set[64] = {};
@@ -440,6 +485,7 @@ int launch_gemm(vitb200_engine *e, int cg, int bn, int epi, const CUtensorMap &t
     if (epi == EPI_BIAS_RESID_F32 && bn == 256 && cg == 2 && p.K >= 2048) // fc2: shallower residual ring, one more operand stage
         return launch_gemm_t<256, EPI_BIAS_RESID_F32, 2, 1>(e, tmA, tmB, tmX, p, s, num_sms);
     VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
+    VB_CASE(256, EPI_BIAS_F16_HILO) VB_CASE(128, EPI_BIAS_F16_HILO)
     VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
     VB_CASE(256, EPI_BIAS_RESID_F32) VB_CASE(128, EPI_BIAS_RESID_F32)
     VB_CASE(256, EPI_PATCH_F32) VB_CASE(128, EPI_PATCH_F32)
@@ -521,7 +567,8 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
     p.n_mtiles = (e->N + 127) / 128;
     p.kv_bytes = (p.NKP * 128 + 1023) / 1024 * 1024;
     p.scale = 1.0f / sqrtf((float)(p.D / p.H));
-    const int smem = 1024 + 2 * (2 * 16384 + 2 * p.kv_bytes) + 8 * 4096 + 256;
+    p.hilo = e->attn_hilo ? 1 : 0;
+    const int smem = attention_tc_smem_bytes(p.kv_bytes);
     static int smem_set[64] = {};
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -542,7 +589,8 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
         CUDA_TRY(cudaMemset(d_trace, 0, 16 * 32 * sizeof(long long)));
         p.trace = d_trace;
     }
-    CUDA_TRY(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATT_TC_THREADS), (size_t)smem, s, e->tmQ, e->tmKV, e->tmAO, p));
+    CUDA_TRY(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATT_TC_THREADS), (size_t)smem, s, e->tmQ, e->tmKV,
+                        e->attn_hilo ? e->tmQl : e->tmQ, e->attn_hilo ? e->tmKVl : e->tmKV, e->tmAO, p));
     CUDA_TRY(cudaGetLastError());
     if (d_trace)
     {
@@ -613,13 +661,18 @@ int tap_f32(float *dst, const float *src, size_t n, cudaStream_t s)
     CUDA_TRY(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
-int tap_f16(float *dst, const __half *src, size_t n, cudaStream_t s)
+int tap_f16(float *dst, const __half *src, size_t n, cudaStream_t s, const __half *lo = nullptr)
 {
     if (!dst) return 0;
     CUDA_TRY(cudaStreamSynchronize(s));
     std::vector<__half> tmp(n);
     CUDA_TRY(cudaMemcpy(tmp.data(), src, n * sizeof(__half), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) dst[i] = __half2float(tmp[i]);
+    if (lo) // split-precision tensor: value = hi + lo
+    {
+        CUDA_TRY(cudaMemcpy(tmp.data(), lo, n * sizeof(__half), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) dst[i] += __half2float(tmp[i]);
+    }
     return 0;
 }
 
@@ -632,6 +685,19 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     const int D = e->hp.hidden_size, N = e->N, T = B * N, C = e->hp.num_classes;
     e->launches = 0;
     __half *PA = e->PA;
+    // the residual epilogue read-modify-writes whole 32-row boxes of X: with a map of exactly T rows the rows of the last M tile
+    // that lie past the batch are zero-filled on load and clipped on store, so nothing outside the batch is ever written
+    if (B != e->max_batch)
+    {
+        auto it = e->tmX_batch.find(B);
+        if (it == e->tmX_batch.end())
+        {
+            CUtensorMap m;
+            if (make_tmap_f32_box32(&m, e->X, (uint64_t)T, (uint64_t)D, (uint64_t)D)) return 1;
+            it = e->tmX_batch.emplace(B, m).first;
+        }
+    }
+    const CUtensorMap &tmX = B == e->max_batch ? e->tmX : e->tmX_batch.find(B)->second;
 
     // patch embedding (vit.cpp:772-797).  P = 16 with CTA pairs: ONE kernel -- the GEMM's A producers gather the f32 pixels
     // straight into the tcgen05 operand tiles (no im2col buffer) and the epilogue adds conv bias + pos_embed and writes token
@@ -650,7 +716,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         p.pos = e->pos; p.np = e->NP; p.ntok = N;
         p.img = d_images; p.S = e->hp.img_size; p.G = e->G;
         ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
-        if (launch_gemm(e, e->cta_group, e->patch.bn, fused_patch ? EPI_PATCH_GATHER_F32 : EPI_PATCH_F32, e->tmA_P, e->patch.tm, e->tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->patch.bn, fused_patch ? EPI_PATCH_GATHER_F32 : EPI_PATCH_F32, e->tmA_P, e->patch.tm, tmX, p, s, e->num_sms)) return 1;
     }
     if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
 
@@ -665,11 +731,11 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         if (tap && tap_f16(taps->ln1, e->A16, (size_t)T * D, s)) return 1;
         {
             GemmParams p{};
-            p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.ldo = 3 * D;
+            p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.out2 = e->QKV16L; p.ldo = 3 * D;
             ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.qkv.bn, EPI_BIAS_F16, e->tmA_D, L.qkv.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
+            if (launch_gemm(e, e->cta_group, L.qkv.bn, e->attn_hilo ? EPI_BIAS_F16_HILO : EPI_BIAS_F16, e->tmA_D, L.qkv.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
         }
-        if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s)) return 1;
+        if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s, e->attn_hilo ? e->QKV16L : nullptr)) return 1;
         {
             ProfScope ps(e, PK_ATTN, 4.0 * B * e->hp.num_attention_heads * (double)N * N * 64, s);
             if (launch_attention(e, B, s)) return 1; // vit.cpp:826-866
@@ -679,7 +745,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = D; p.K = D; p.bias = L.proj.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_PROJ, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
+            if (launch_gemm(e, e->cta_group, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
         }
         if (tap && tap_f32(taps->x1, e->X, (size_t)T * D, s)) return 1;
         {
@@ -691,14 +757,14 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D;
             ProfScope ps(e, PK_FC1, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
+            if (launch_gemm(e, e->cta_group, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
         }
         if (tap && tap_f16(taps->h, e->H16, (size_t)T * 4 * D, s)) return 1;
         {
             GemmParams p{};
             p.M = T; p.N = D; p.K = 4 * D; p.bias = L.fc2.b; p.out = e->X; p.ldo = D; p.resid = e->X;
             ProfScope ps(e, PK_FC2, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, e->tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
+            if (launch_gemm(e, e->cta_group, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
         }
         if (tap && tap_f32(taps->x2, e->X, (size_t)T * D, s)) return 1;
     }
@@ -709,16 +775,23 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     const int TH = e->head_tokens, R = B * TH;
     if (launch_layernorm(e, e->X, (size_t)D, e->norm_w, e->norm_b, e->CLS16, R, s, TH, (size_t)N * D)) return 1;
     if (taps && tap_f16(taps->final_ln, e->CLS16, (size_t)R * D, s)) return 1;
-    float *lg = d_logits ? d_logits : e->d_logits;
+    // internal logits rows have pitch Cp (num_classes padded to 4; the padded W rows are TMA zero fill, the padded bias is 0);
+    // a caller's dense [rows][num_classes] buffer is written directly when the two coincide, else through a 2-D copy
+    const int Cp = e->Cp;
+    float *lg = (d_logits && Cp == C) ? d_logits : e->d_logits;
     {
         GemmParams p{};
-        p.M = R; p.N = C; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = C;
-        ProfScope ps(e, PK_HEAD, 2.0 * p.M * p.N * p.K, s);
-        if (launch_gemm(e, e->cta_group, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, e->tmX, p, s, e->num_sms)) return 1;
+        p.M = R; p.N = Cp; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = Cp;
+        ProfScope ps(e, PK_HEAD, 2.0 * p.M * C * p.K, s);
+        if (launch_gemm(e, e->cta_group, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, tmX, p, s, e->num_sms)) return 1;
     }
+    if (d_logits && lg != d_logits)
+        CUDA_TRY(cudaMemcpy2DAsync(d_logits, (size_t)C * 4, lg, (size_t)Cp * 4, (size_t)C * 4, (size_t)R, cudaMemcpyDeviceToDevice, s));
     if (d_probs || (k > 0 && (d_topk_idx || d_topk_val)))
     {
-        softmax_topk_kernel<<<R, 256, (size_t)C * sizeof(float), s>>>(lg, d_probs, d_topk_idx, d_topk_val, C, k);
+        const size_t row_bytes = (size_t)C * sizeof(float);
+        float *scratch = row_bytes > kSoftmaxSmemMax ? e->d_sm_scratch : nullptr;
+        softmax_topk_kernel<<<R, 256, scratch ? 0 : row_bytes, s>>>(lg, Cp, d_probs, d_topk_idx, d_topk_val, C, k, scratch);
         CUDA_TRY(cudaGetLastError());
         e->launches++;
     }
@@ -785,11 +858,30 @@ int vitb200_create(const vitb200_hparams *hp, const vitb200_tensor *t, int n, in
     return vitb200_create_ex(hp, t, n, device, max_batch, 1, out);
 }
 
+// The C ABI promises "non-zero return, never abort": nothing may unwind through an extern "C" frame.  Host-side allocations
+// (std::vector staging buffers sized from a model file) can throw; every entry point that owns such code runs it through this.
+#define VB_NOEXCEPT_BEGIN try {
+#define VB_NOEXCEPT_END(cleanup)                                                                          \
+    } catch (const std::exception &ex) { cleanup; return fail("%s: %s", __func__, ex.what()); }            \
+    catch (...) { cleanup; return fail("%s: unknown exception", __func__); }
+
+static int create_impl(const vitb200_hparams *hp, const vitb200_tensor *t, int n, int device, int max_batch, int head_tokens,
+                       vitb200_engine *&e, vitb200_engine **out);
+
 int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n, int device, int max_batch, int head_tokens,
                       vitb200_engine **out)
 {
     if (!hp || !t || !out) return fail("vitb200_create: null argument");
     *out = nullptr;
+    vitb200_engine *e = nullptr;
+    VB_NOEXCEPT_BEGIN
+    return create_impl(hp, t, n, device, max_batch, head_tokens, e, out);
+    VB_NOEXCEPT_END(if (e) vitb200_destroy(e))
+}
+
+static int create_impl(const vitb200_hparams *hp, const vitb200_tensor *t, int n, int device, int max_batch, int head_tokens,
+                       vitb200_engine *&e, vitb200_engine **out)
+{
     // hyper-parameter sanity first (no division by a field a corrupt file may have zeroed; no device needed to reject them)
     if (hp->hidden_size < 64 || hp->hidden_size > 8192 || hp->num_hidden_layers < 1 || hp->num_hidden_layers > 4096 ||
         hp->num_attention_heads < 1 || hp->num_attention_heads > 128 || hp->num_classes < 1 || hp->num_classes > (1 << 20) ||
@@ -808,10 +900,10 @@ int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n,
         return fail("head dim %d not supported (64 only)", hp->num_attention_heads ? hp->hidden_size / hp->num_attention_heads : 0);
     if (hp->hidden_size % 64 != 0) return fail("hidden size %d must be a multiple of 64", hp->hidden_size);
     if (hp->img_size % hp->patch_size != 0) return fail("img_size %d not a multiple of patch_size %d", hp->img_size, hp->patch_size);
-    if (hp->num_classes % 4 != 0) return fail("num_classes %d must be a multiple of 4", hp->num_classes);
     if (max_batch < 1) return fail("max_batch must be >= 1");
+    if (check_unique_names(t, n)) return 1;
 
-    vitb200_engine *e = new vitb200_engine();
+    e = new vitb200_engine();
     e->hp = *hp;
     if (e->hp.eps <= 0.f) e->hp.eps = 1e-6f;
     e->device = device;
@@ -828,30 +920,32 @@ int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n,
         if (!pw || nelem(pw) % per_c != 0 || (nelem(pw) / per_c != 1 && nelem(pw) / per_c != 3))
         {
             delete e;
+            e = nullptr;
             return fail("tensor 'patch_embed.proj.weight' is missing or is not a 1- or 3-channel %dx%d kernel", P, P);
         }
         e->C = (int)(nelem(pw) / per_c);
     }
-    if (head_tokens < 1 || head_tokens > e->N) { const int ntok = e->N; delete e; return fail("head_tokens %d out of range (1..%d)", head_tokens, ntok); }
+    if (head_tokens < 1 || head_tokens > e->N) { const int ntok = e->N; delete e; e = nullptr; return fail("head_tokens %d out of range (1..%d)", head_tokens, ntok); }
     e->head_tokens = head_tokens;
+    e->Cp = (hp->num_classes + 3) / 4 * 4;
     e->KP = e->C * P * P;
     e->KPp = (e->KP + 63) / 64 * 64;
     e->cta_group = (getenv("VITB200_CTA_GROUP") && atoi(getenv("VITB200_CTA_GROUP")) == 1) ? 1 : 2;
     e->use_graph = !(getenv("VITB200_GRAPH") && atoi(getenv("VITB200_GRAPH")) == 0);
-    auto bail = [&](int) { vitb200_destroy(e); return 1; };
+    auto bail = [&](int) { vitb200_destroy(e); e = nullptr; return 1; };
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
 
     // ---- weights (names: reference vit.cpp:518-579)
-    if (upload_f32(e, t, n, "cls_token", D, &e->cls)) return bail(1);
-    if (upload_f32(e, t, n, "pos_embed", (int64_t)D * e->N, &e->pos)) return bail(1);
-    if (upload_linear(e, t, n, "patch_embed.proj.weight", "patch_embed.proj.bias", D, e->KP, e->KPp, &e->patch)) return bail(1);
+    if (upload_f32(e, t, n, "cls_token", D, 1, 1, 1, &e->cls)) return bail(1);
+    if (upload_f32(e, t, n, "pos_embed", D, e->N, 1, 1, &e->pos)) return bail(1);
+    if (upload_linear(e, t, n, "patch_embed.proj.weight", "patch_embed.proj.bias", D, e->KP, e->KPp, &e->patch, P)) return bail(1);
     e->layers.resize(hp->num_hidden_layers);
     for (int i = 0; i < hp->num_hidden_layers; ++i)
     {
         Layer &L = e->layers[i];
         const std::string p = "blocks." + std::to_string(i) + ".";
-        if (upload_f32(e, t, n, p + "norm1.weight", D, &L.n1w) || upload_f32(e, t, n, p + "norm1.bias", D, &L.n1b) ||
-            upload_f32(e, t, n, p + "norm2.weight", D, &L.n2w) || upload_f32(e, t, n, p + "norm2.bias", D, &L.n2b))
+        if (upload_f32(e, t, n, p + "norm1.weight", D, 1, 1, 1, &L.n1w) || upload_f32(e, t, n, p + "norm1.bias", D, 1, 1, 1, &L.n1b) ||
+            upload_f32(e, t, n, p + "norm2.weight", D, 1, 1, 1, &L.n2w) || upload_f32(e, t, n, p + "norm2.bias", D, 1, 1, 1, &L.n2b))
             return bail(1);
         if (upload_linear(e, t, n, p + "attn.qkv.weight", p + "attn.qkv.bias", 3 * D, D, D, &L.qkv) ||
             upload_linear(e, t, n, p + "attn.proj.weight", p + "attn.proj.bias", D, D, D, &L.proj) ||
@@ -859,7 +953,7 @@ int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n,
             upload_linear(e, t, n, p + "mlp.fc2.weight", p + "mlp.fc2.bias", D, 4 * D, 4 * D, &L.fc2))
             return bail(1);
     }
-    if (upload_f32(e, t, n, "norm.weight", D, &e->norm_w) || upload_f32(e, t, n, "norm.bias", D, &e->norm_b)) return bail(1);
+    if (upload_f32(e, t, n, "norm.weight", D, 1, 1, 1, &e->norm_w) || upload_f32(e, t, n, "norm.bias", D, 1, 1, 1, &e->norm_b)) return bail(1);
     if (upload_linear(e, t, n, "head.weight", "head.bias", hp->num_classes, D, D, &e->head)) return bail(1);
 
     // ---- activation arena
@@ -873,11 +967,19 @@ int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n,
     const size_t img_elems = (size_t)e->C * hp->img_size * hp->img_size; // per image
     if (dev_alloc(e, &e->d_img, B * img_elems) || dev_alloc(e, &e->X, T * D) ||
         dev_alloc(e, &e->A16, T * D) || dev_alloc(e, &e->QKV16, T * 3 * D) || dev_alloc(e, &e->H16, h16) ||
-        dev_alloc(e, &e->CLS16, R * D) || dev_alloc(e, &e->d_logits, R * hp->num_classes) ||
+        dev_alloc(e, &e->CLS16, R * D) || dev_alloc(e, &e->d_logits, R * e->Cp) || dev_alloc(e, &e->d_logits_slot[0], R * hp->num_classes) ||
         dev_alloc(e, &e->d_probs, R * hp->num_classes) || dev_alloc(e, &e->d_topk_idx, R * e->max_k) ||
         dev_alloc(e, &e->d_topk_val, R * e->max_k))
         return bail(1);
-    e->d_img_slot[0] = e->d_img; e->d_probs_slot[0] = e->d_probs; e->d_logits_slot[0] = e->d_logits;
+    e->d_img_slot[0] = e->d_img; e->d_probs_slot[0] = e->d_probs;
+    {
+        // soft-max working row: dynamic shared memory up to the per-CTA limit (opt-in above 48 KB), global scratch beyond it
+        const size_t row_bytes = (size_t)hp->num_classes * sizeof(float);
+        if (row_bytes > kSoftmaxSmemMax) { if (dev_alloc(e, &e->d_sm_scratch, R * hp->num_classes)) return bail(1); }
+        else if (row_bytes > 48 * 1024 &&
+                 cudaFuncSetAttribute(softmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSoftmaxSmemMax) != cudaSuccess)
+            return bail(fail("cudaFuncSetAttribute(softmax_topk_kernel) failed"));
+    }
     e->d_topk_idx_slot[0] = e->d_topk_idx; e->d_topk_val_slot[0] = e->d_topk_val;
     if (dev_alloc(e, &e->d_img_slot[1], B * img_elems) || dev_alloc(e, &e->d_probs_slot[1], R * hp->num_classes) ||
         dev_alloc(e, &e->d_logits_slot[1], R * hp->num_classes) || dev_alloc(e, &e->d_topk_idx_slot[1], R * e->max_k) ||
@@ -917,10 +1019,20 @@ int vitb200_create_ex(const vitb200_hparams *hp, const vitb200_tensor *t, int n,
                 make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP) ||
                 make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)e->N, (uint64_t)D))
                 return bail(1);
+            // split-precision q, k, v (reference: f32 operands, vit.cpp:848,858); VITB200_ATTN_HILO=0 keeps the f16-only operands
+            e->attn_hilo = !(getenv("VITB200_ATTN_HILO") && atoi(getenv("VITB200_ATTN_HILO")) == 0);
+            if (e->attn_hilo)
+            {
+                if (dev_alloc(e, &e->QKV16L, T * 3 * D) ||
+                    make_tmap(&e->tmQl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
+                    make_tmap(&e->tmKVl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP))
+                    return bail(1);
+            }
         }
     }
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail("device sync after upload failed"));
     *out = e;
+    e = nullptr; // ownership passed to the caller
     return 0;
 }
 
@@ -987,7 +1099,24 @@ int vitb200_profile_read(vitb200_engine *e, int kind, double *ms_total, int *lau
     *ms_total = ms; *launches = n; *flops_per_launch = fl;
     return 0;
 }
+static int test_attention_impl(int device, int kernel, int B, int N, int H, const uint16_t *qkv, const uint16_t *qkv_lo, float *out);
+
 int vitb200_test_attention(int device, int kernel, int B, int N, int H, const uint16_t *qkv, float *out)
+{
+    VB_NOEXCEPT_BEGIN
+    return test_attention_impl(device, kernel, B, N, H, qkv, nullptr, out);
+    VB_NOEXCEPT_END((void)0)
+}
+
+int vitb200_test_attention_hilo(int device, int B, int N, int H, const uint16_t *qkv_hi, const uint16_t *qkv_lo, float *out)
+{
+    if (!qkv_lo) return fail("bad argument");
+    VB_NOEXCEPT_BEGIN
+    return test_attention_impl(device, 2, B, N, H, qkv_hi, qkv_lo, out);
+    VB_NOEXCEPT_END((void)0)
+}
+
+static int test_attention_impl(int device, int kernel, int B, int N, int H, const uint16_t *qkv, const uint16_t *qkv_lo, float *out)
 {
     if (!qkv || !out || B < 1 || N < 1 || H < 1) return fail("bad argument");
     int ndev = 0;
@@ -1008,6 +1137,13 @@ int vitb200_test_attention(int device, int kernel, int B, int N, int H, const ui
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("stream creation failed"));
     if (dev_alloc(e, &e->QKV16, (size_t)T * 3 * D) || dev_alloc(e, &e->A16, (size_t)T * D)) return bail(1);
     if (cudaMemcpy(e->QKV16, qkv, (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
+    if (qkv_lo)
+    {
+        if (N > 224) return bail(fail("split-precision attention needs N <= 224"));
+        if (dev_alloc(e, &e->QKV16L, (size_t)T * 3 * D)) return bail(1);
+        if (cudaMemcpy(e->QKV16L, qkv_lo, (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
+        e->attn_hilo = true;
+    }
     if (kernel == 0) kernel = N <= 224 ? 2 : (N <= ATT_LONG_MAX_KEYS ? 3 : 1);
     if (kernel == 2 && N > 224) return bail(fail("tcgen05 single-block attention needs N <= 224"));
     if (kernel == 3 && (N <= 112 || N > ATT_LONG_MAX_KEYS)) return bail(fail("tcgen05 two-sweep attention needs 112 < N <= %d", ATT_LONG_MAX_KEYS));
@@ -1020,6 +1156,9 @@ int vitb200_test_attention(int device, int kernel, int B, int N, int H, const ui
             make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)(NKP <= 224 ? NKP : 64)) ||
             make_tmap(&e->tmKV64, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 64) ||
             make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)N, (uint64_t)D))
+            return bail(1);
+        if (qkv_lo && (make_tmap(&e->tmQl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
+                       make_tmap(&e->tmKVl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP)))
             return bail(1);
     }
     if (launch_attention(e, B, e->stream)) return bail(1);
@@ -1064,6 +1203,7 @@ static int forward_enqueue(vitb200_engine *e, const float *images, int batch, fl
 {
     if (!e || !images) return fail("null argument");
     if (batch < 1 || batch > e->max_batch) return fail("batch %d out of range (1..%d)", batch, e->max_batch);
+    if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k); // before anything is enqueued
     CUDA_TRY(cudaSetDevice(e->device));
     const int sl = (int)(e->submits & 1);
     cudaStream_t s = e->stream, cs = e->copy_stream;
@@ -1075,7 +1215,6 @@ static int forward_enqueue(vitb200_engine *e, const float *images, int batch, fl
     CUDA_TRY(cudaEventRecord(e->ev_h2d[sl], cs));
     CUDA_TRY(cudaStreamWaitEvent(s, e->ev_h2d[sl], 0));
     const bool want_topk = k > 0 && (topk_idx || topk_prob);
-    if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
     float *dp = (probs || want_topk) ? e->d_probs_slot[sl] : nullptr;
     int32_t *di = want_topk ? e->d_topk_idx_slot[sl] : nullptr;
     float *dv = want_topk ? e->d_topk_val_slot[sl] : nullptr;
@@ -1123,6 +1262,18 @@ int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const
     if (!engines || n_engines < 1 || !images) return fail("null argument");
     const vitb200_engine *e0 = engines[0];
     if (!e0) return fail("null engine");
+    if (k < 0 || k > e0->max_k) return fail("k %d out of range (0..%d)", k, e0->max_k);
+    {
+        // validate every shard before the first one is enqueued
+        const int base0 = batch / n_engines, rem0 = batch % n_engines;
+        for (int g = 0; g < n_engines; ++g)
+        {
+            const int cnt = base0 + (g < rem0 ? 1 : 0);
+            if (cnt == 0) continue;
+            if (!engines[g]) return fail("null engine %d", g);
+            if (cnt > engines[g]->max_batch) return fail("shard %d: batch %d out of range (1..%d)", g, cnt, engines[g]->max_batch);
+        }
+    }
     const size_t img_elems = (size_t)e0->C * e0->hp.img_size * e0->hp.img_size;
     const size_t C = (size_t)e0->hp.num_classes * e0->head_tokens; // output floats per image
     const size_t kk = (size_t)k * e0->head_tokens;                 // top-k entries per image
@@ -1139,7 +1290,14 @@ int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const
         if (vitb200_forward_async(engines[g], images + (size_t)begin * img_elems, cnt, probs ? probs + (size_t)begin * C : nullptr,
                                   logits ? logits + (size_t)begin * C : nullptr, topk_idx ? topk_idx + (size_t)begin * kk : nullptr,
                                   topk_prob ? topk_prob + (size_t)begin * kk : nullptr, k))
+        {
+            // shards already enqueued are copying into the caller's buffers: drain them before reporting the failure
+            const std::string first = g_err;
+            for (int h = 0; h < g; ++h)
+                if (engines[h]) (void)vitb200_sync(engines[h]);
+            g_err = first;
             return 1;
+        }
         begin += cnt;
     }
     int rc = 0;
@@ -1201,13 +1359,13 @@ int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const in
     const int C = e->hp.num_classes;
     if (probs || logits || want_topk)
     {
-        if (run_forward_graphed(e, e->d_img, batch, (probs || want_topk) ? e->d_probs : nullptr, e->d_logits, want_topk ? e->d_topk_idx : nullptr,
+        if (run_forward_graphed(e, e->d_img, batch, (probs || want_topk) ? e->d_probs : nullptr, e->d_logits_slot[0], want_topk ? e->d_topk_idx : nullptr,
                                 want_topk ? e->d_topk_val : nullptr, want_topk ? k : 0, s))
             return 1;
         e->launches += 1;
         const size_t rows = (size_t)batch * e->head_tokens;
         if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs, rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits, rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits_slot[0], rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx, rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val, rows * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
@@ -1226,8 +1384,9 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
     __half *dA = nullptr, *dW = nullptr;
     float *dB = nullptr, *dR = nullptr;
     void *dO = nullptr;
-    const bool f16out = epilogue == EPI_BIAS_F16 || epilogue == EPI_BIAS_GELU_F16;
+    const bool f16out = epilogue == EPI_BIAS_F16 || epilogue == EPI_BIAS_GELU_F16 || epilogue == EPI_BIAS_F16_HILO;
     const size_t osz = (size_t)M * N * (f16out ? 2 : 4);
+    void *dO2 = nullptr;
     int rc = 1;
     do
     {
@@ -1236,6 +1395,11 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
         cudaMemcpy(dW, W, (size_t)N * K * 2, cudaMemcpyHostToDevice);
         cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice);
         cudaMemset(dO, 0, osz);
+        if (epilogue == EPI_BIAS_F16_HILO)
+        {
+            if (cudaMalloc(&dO2, osz)) { fail("cudaMalloc failed"); break; }
+            cudaMemset(dO2, 0, osz);
+        }
         if (epilogue == EPI_BIAS_RESID_F32)
         {
             if (!resid) { fail("resid required"); break; }
@@ -1254,7 +1418,7 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
             if (make_tmap_f32_box32(&tX, dO, M, N, N)) break;
         }
         GemmParams p{};
-        p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.ldo = N; p.resid = (const float *)dO;
+        p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.out2 = dO2; p.ldo = N; p.resid = (const float *)dO;
         if (launch_gemm(nullptr, cg, bn, epilogue, tA, tB, tX, p, 0, prop.multiProcessorCount)) break;
         cudaError_t err = cudaDeviceSynchronize();
         if (err != cudaSuccess) { fail("GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
@@ -1263,12 +1427,17 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
             std::vector<__half> tmp((size_t)M * N);
             cudaMemcpy(tmp.data(), dO, osz, cudaMemcpyDeviceToHost);
             for (size_t i = 0; i < tmp.size(); ++i) out[i] = __half2float(tmp[i]);
+            if (dO2) // split-precision result: hi + lo (exact in f32: the two parts do not overlap)
+            {
+                cudaMemcpy(tmp.data(), dO2, osz, cudaMemcpyDeviceToHost);
+                for (size_t i = 0; i < tmp.size(); ++i) out[i] += __half2float(tmp[i]);
+            }
         }
         else
             cudaMemcpy(out, dO, osz, cudaMemcpyDeviceToHost);
         rc = 0;
     } while (0);
-    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dO); cudaFree(dR);
+    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dO); cudaFree(dR); cudaFree(dO2);
     return rc;
 }
 
@@ -1287,10 +1456,16 @@ extern "C" int vitb200_create_from_file(const char *path, int device, int max_ba
 extern "C" int vitb200_create_from_file_ex(const char *path, int device, int max_batch, int head_tokens, vitb200_engine **out)
 {
     if (!path || !out) return fail("null argument");
+    *out = nullptr;
+    VB_NOEXCEPT_BEGIN
     std::ifstream fin(path, std::ios::binary);
     if (!fin) return fail("failed to open '%s'", path);
     fin.seekg(0, std::ios::end);
-    const size_t fsize = (size_t)fin.tellg();
+    const std::streamoff fend = fin.tellg();
+    // a directory or an unseekable stream reports -1; model files beyond 64 GiB are not something this loader stages in host memory
+    if (!fin || fend < 0) return fail("failed to read '%s' (not a regular file)", path);
+    if ((unsigned long long)fend > (64ull << 30)) return fail("model file '%s' is too large (%lld bytes)", path, (long long)fend);
+    const size_t fsize = (size_t)fend;
     fin.seekg(0);
     std::vector<char> buf(fsize);
     fin.read(buf.data(), (std::streamsize)fsize);
@@ -1326,4 +1501,5 @@ extern "C" int vitb200_create_from_file_ex(const char *path, int device, int max
     int rc = vitb200_create_ex(&hp, ts.data(), (int)ts.size(), device, max_batch, head_tokens, out);
     if (rc == 0) (*out)->labels = labels;
     return rc;
+    VB_NOEXCEPT_END(if (*out) { vitb200_destroy(*out); *out = nullptr; })
 }

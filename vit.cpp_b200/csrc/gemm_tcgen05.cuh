@@ -6,12 +6,17 @@
 // Numerics follow the reference recipe: A = activations already rounded to f16 (RNE, ggml.c:9493-9506),
 // W = the f16 weights as stored in the model file (ne0 = K contiguous, vit.cpp:531-543), fp32 accumulation.
 //
-// Structure (sm_100a): persistent CTAs, one per SM, 6 warps:
-//   warp 0   TMA producer  : cp.async.bulk.tensor 128x64 A tile + BNx64 W tile per stage (SWIZZLE_128B)
-//   warp 1   MMA issuer    : one thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16) x4 per stage,
-//                            accumulators in TMEM (2 x BN columns, double buffered against the epilogue)
-//   warps 2-5 epilogue     : tcgen05.ld -> registers -> (bias / GELU / residual / pos-embed) -> swizzled smem
-//                            transpose -> 128-bit fully coalesced global stores
+// Structure (sm_100a): persistent CTA PAIRS (cluster 2x1x1, one pair per TPC; CG = 1 keeps a single-CTA variant), each pair
+// computing 256 x BN tiles of C with tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA, W tile split along N between the CTAs):
+//   warp 0        TMA producer : cp.async.bulk.tensor -- this CTA's 128 x 64 A tile + its HALF of the BN x 64 W tile per stage
+//                                (SWIZZLE_128B), transaction bytes of both CTAs collected on the leader's mbarrier
+//   warp 1        MMA issuer   : leader CTA only; warp-uniform loop, one elected lane issues 4 x tcgen05.mma.kind::f16 (K = 16) per
+//                                stage; accumulators in TMEM (2 x BN columns, double buffered against the epilogue); smem slots and
+//                                accumulators are released to BOTH CTAs by multicast tcgen05.commit
+//   warps 2-5     (EPI_PATCH_GATHER_F32 only) A producers: gather f32 pixels -> f16 swizzled operand tiles, no im2col buffer
+//   next 8 warps  epilogue     : tcgen05.ld -> registers -> bias / GELU / hi-lo split -> XOR-swizzled smem transpose -> 128-bit
+//                                coalesced stores (two warps per TMEM lane quarter, alternating column passes)
+//   or 4 warps    residual epilogue (proj, fc2): per-warp TMA ring streams the f32 residual tile in, adds in place, TMA-stores
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #pragma once
 #include "ptx.cuh"
@@ -26,6 +31,9 @@ enum GemmEpilogue
     EPI_PATCH_F32 = 3,      // out f32[token row] = (acc + bias) + pos_embed           (patch embed; vit.cpp:773-797)
     EPI_BIAS_F32 = 4,       // out f32 = acc + bias                                   (head logits)
     EPI_PATCH_GATHER_F32 = 5, // EPI_PATCH_F32 with the A operand gathered straight from the f32 HWC pixels (P = 16): no im2col buffer
+    EPI_BIAS_F16_HILO = 6,  // x = acc + bias kept to ~22 significant bits as TWO f16 tensors: out = hi = f16(x), out2 = lo = f16(x - hi)
+                            // (qkv in front of the tcgen05 attention: the reference feeds f32 q, k, v to both attention mat-muls,
+                            // vit.cpp:848,858; hi + lo lets the f16 tensor cores reproduce that with split-precision MMAs)
 };
 
 struct GemmParams
@@ -33,6 +41,7 @@ struct GemmParams
     int M, N, K;        // valid extents (rows of A / rows of W / reduction)
     const float *bias;  // [N]
     void *out;          // f16 or f32, row-major, leading dimension ldo
+    void *out2;         // EPI_BIAS_F16_HILO: the lo halves, same shape as out
     int ldo;
     const float *resid; // EPI_BIAS_RESID_F32: [M][ldo] (may alias out)
     const float *pos;   // EPI_PATCH_F32: pos_embed [ntok][N]
@@ -52,7 +61,12 @@ constexpr int GEMM_BK = 64;
 // traffic of the B operand -- the 1-CTA kernel is shared-memory-bandwidth bound at ~70 % tensor-pipe utilisation.
 // kDeepK (fc2, K = 4 D): the main loop of a tile is long, so a shallower residual ring (2 loads in flight per warp) still keeps up
 // and its shared memory buys a fifth operand stage, which is what the tensor pipe is short of there.
-template <int BN, bool kResid, int CG, bool kGather = false, bool kDeepK = false>
+// kF16Out (qkv, fc1): the bias is applied in the row-per-thread domain, i.e. every lane needs the same 64 values per column pass.  With
+// 227 KB of shared memory carved out the SM has practically no L1, so reading them with __ldg put an L2 round trip (~300 clocks) in
+// front of every 8-column chunk (ncu: long-scoreboard stalls on LDG.CONSTANT dominated the epilogue and capped the split-precision
+// qkv epilogue at 56 % tensor-pipe activity).  Each epilogue warp therefore keeps the <= 128 bias values of its column passes in a
+// private 512-B shared-memory strip, loaded one tile ahead (one 16-B load per lane, latency hidden behind the accumulator wait).
+template <int BN, bool kResid, int CG, bool kGather = false, bool kDeepK = false, bool kF16Out = false>
 struct GemmCfg
 {
     static constexpr int kResidRing = kDeepK ? 3 : 5;
@@ -67,11 +81,12 @@ struct GemmCfg
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = kResid ? 4 * kResidRing * 4096 : kEpiWarps * 4096; // per epilogue warp: ring or transpose buffer
     static constexpr int BAR_BYTES = 512;
+    static constexpr int BIAS_BYTES = kF16Out ? kEpiWarps * 512 : 0; // per-warp bias strips (f16 epilogues)
     static constexpr int kSmemLimit = 232448; // 227 KB per CTA
-    static constexpr int kStagesFit = (kSmemLimit - 1024 - STAGE_BYTES - BAR_BYTES) / (A_BYTES + B_BYTES);
+    static constexpr int kStagesFit = (kSmemLimit - 1024 - STAGE_BYTES - BAR_BYTES - BIAS_BYTES) / (A_BYTES + B_BYTES);
     static constexpr int kStagesFit8 = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kStages = kGather ? kStagesFit8 / 3 * 3 : kStagesFit8; // operand ring depth: whatever fits (gather fills 3 at a time)
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * (A_BYTES + B_BYTES) + STAGE_BYTES + BAR_BYTES;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * (A_BYTES + B_BYTES) + STAGE_BYTES + BAR_BYTES + BIAS_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
@@ -89,18 +104,20 @@ __device__ __forceinline__ float gelu_tanh_f32(float x)
 }
 
 template <int BN, int EPI, int DEEPK, int CG>
-__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0>::kThreads), 1)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0,
+                                           EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_F16_HILO>::kThreads), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const GemmParams p)
 {
     constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32);
     constexpr bool kGather = (EPI == EPI_PATCH_GATHER_F32);
     constexpr bool kPatch = (EPI == EPI_PATCH_F32 || EPI == EPI_PATCH_GATHER_F32);
-    using Cfg = GemmCfg<BN, kResid, CG, kGather, DEEPK != 0>;
+    constexpr bool kOutF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_F16_HILO);
+    constexpr bool kHiLo = (EPI == EPI_BIAS_F16_HILO);
+    using Cfg = GemmCfg<BN, kResid, CG, kGather, DEEPK != 0, kOutF16>;
     static_assert(!kGather || (CG == 2 && Cfg::kStages % 3 == 0 && Cfg::kStages >= 3), "gathered patch embedding: CTA pairs, stages in threes");
     constexpr int TILE_M = GEMM_BM * CG; // rows of C per CTA group
     constexpr int kStages = Cfg::kStages;
-    constexpr bool kOutF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16);
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B wants 1024-B aligned tiles
@@ -423,11 +440,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         {
         uint8_t *stg = stg_base + (warp_idx - Cfg::kFirstEpiWarp) * 4096;
         const int half_sel = (warp_idx - Cfg::kFirstEpiWarp) >> 2; // warps w and w+4 share a TMEM lane quarter and alternate column passes
+        // f16 epilogues: this warp's bias strip.  Lane l holds (and pre-loads, one tile ahead) the 4 bias values of columns
+        // 4 (l & 15) .. +3 of the warp's column pass half_sel + 2 (l >> 4); the strip is [pass][16 x float4].
+        float4 *bias_s4 = reinterpret_cast<float4 *>(smem + kStages * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STAGE_BYTES + Cfg::BAR_BYTES) +
+                          (warp_idx - Cfg::kFirstEpiWarp) * 32;
+        auto load_bias = [&](int tile) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (kOutF16)
+            {
+                const int cp = half_sel + 2 * (lane >> 4);
+                const int col = (tile % n_tiles) * BN + cp * 64 + (lane & 15) * 4;
+                if (tile < num_tiles && cp < BN / 64 && col < p.N) b = __ldg(reinterpret_cast<const float4 *>(p.bias + col)); // N % 8 == 0
+            }
+            return b;
+        };
+        float4 bias_next = load_bias(group_id);
         for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it)
         {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
+            if constexpr (kOutF16)
+            {
+                bias_s4[lane] = bias_next;             // every lane is past the previous tile's reads (__syncwarp at the end of its last pass)
+                __syncwarp();
+                bias_next = load_bias(tile + num_groups); // in flight while this tile's accumulator is awaited and processed
+            }
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tcgen05_fence_after();
             const int m0 = m_blk * TILE_M + (int)cta_rank * GEMM_BM + q * 32;
@@ -462,20 +500,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
                 if constexpr (kOutF16)
                 {
-                    // math in the row-per-thread domain (bias is warp-uniform -> broadcast loads), pack to f16
+                    // math in the row-per-thread domain (bias is warp-uniform -> broadcast loads), pack to f16.  The hi-lo epilogue
+                    // runs the staging round trip twice over the same accumulator registers: part 0 emits hi = f16(x), part 1
+                    // recomputes x and hi and emits lo = f16(x - hi) (exact difference, |lo| <= 2^-11 |x|) to the second tensor.
                     uint4 *stg4 = reinterpret_cast<uint4 *>(stg);
+#pragma unroll
+                    for (int part = 0; part < (kHiLo ? 2 : 1); ++part)
+                    {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) // 8 chunks of 8 columns (16 B of f16)
                     {
                         uint32_t packed[4];
-                        float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        if (n0 + c + j * 8 < p.N) // N % 8 == 0 for f16 outputs: a chunk of 8 columns is all-in or all-out
-                        {
-                            const float4 bl = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + j * 8));
-                            const float4 bh = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c + j * 8 + 4));
-                            bias8[0] = bl.x; bias8[1] = bl.y; bias8[2] = bl.z; bias8[3] = bl.w;
-                            bias8[4] = bh.x; bias8[5] = bh.y; bias8[6] = bh.z; bias8[7] = bh.w;
-                        }
+                        // the strip holds zeros for columns >= N (N % 8 == 0 for f16 outputs: a chunk of 8 columns is all-in or all-out)
+                        const float4 bl = bias_s4[(cp >> 1) * 16 + j * 2], bh = bias_s4[(cp >> 1) * 16 + j * 2 + 1];
+                        const float bias8[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                         {
@@ -492,12 +530,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             else
                             {
                                 h = __floats2half2_rn(x0, x1);
+                                if (kHiLo && part == 1)
+                                {
+                                    const float2 hf = __half22float2(h);
+                                    h = __floats2half2_rn(__fsub_rn(x0, hf.x), __fsub_rn(x1, hf.y));
+                                }
                             }
                             packed[e] = *reinterpret_cast<uint32_t *>(&h);
                         }
                         stg4[lane * 8 + (j ^ sw)] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                     }
                     __syncwarp();
+                    __half *dst = reinterpret_cast<__half *>(part == 0 ? p.out : p.out2);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                     {
@@ -507,9 +551,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const int grow = m0 + row;
                         const int gcol = n0 + c + ch * 8;
                         if (grow < p.M && gcol < p.N)
-                            *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out) + (size_t)grow * p.ldo + gcol) = val;
+                            *reinterpret_cast<uint4 *>(dst + (size_t)grow * p.ldo + gcol) = val;
                     }
                     __syncwarp();
+                    }
                 }
                 else
                 {

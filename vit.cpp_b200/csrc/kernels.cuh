@@ -292,16 +292,20 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int N
 }
 
 // ------------------------------------------------------------------------------------------------
-// One CTA per image: probs = softmax(logits) with the reference's f16-exp semantics, then top-k
-// (value descending, index ascending on ties) by k rounds of block arg-max.
-__global__ void softmax_topk_kernel(const float *__restrict__ logits, float *__restrict__ probs, int32_t *__restrict__ topk_idx,
-                                    float *__restrict__ topk_val, int C, int k)
+// One CTA per classifier row: probs = softmax(logits) with the reference's f16-exp semantics, then top-k (value descending, index
+// ascending on ties) by k rounds of block arg-max.  logits rows have pitch ldl (>= C: the head GEMM pads the class count to a
+// multiple of 4), probs rows are dense.  The working copy of the row lives in dynamic shared memory when C floats fit (the
+// launcher opts in up to the 227 KB limit), otherwise in `scratch` (global, [rows][C]); entries r >= C of a top-k list (k > C)
+// are (-1, 0).
+__global__ void softmax_topk_kernel(const float *__restrict__ logits, int ldl, float *__restrict__ probs, int32_t *__restrict__ topk_idx,
+                                    float *__restrict__ topk_val, int C, int k, float *__restrict__ scratch)
 {
-    extern __shared__ float sp[];
+    extern __shared__ float sp_smem[];
     __shared__ float red_v[32];
     __shared__ int red_i[32];
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const float *lg = logits + (size_t)img * C;
+    float *sp = scratch ? scratch + (size_t)img * C : sp_smem;
+    const float *lg = logits + (size_t)img * ldl;
     float mx = -INFINITY;
     for (int i = tid; i < C; i += blockDim.x) { const float v = lg[i]; sp[i] = v; mx = fmaxf(mx, v); }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -333,6 +337,15 @@ __global__ void softmax_topk_kernel(const float *__restrict__ logits, float *__r
     __syncthreads();
     for (int r = 0; r < k; ++r)
     {
+        if (r >= C) // fewer classes than requested entries
+        {
+            if (tid == 0)
+            {
+                if (topk_idx) topk_idx[(size_t)img * k + r] = -1;
+                if (topk_val) topk_val[(size_t)img * k + r] = 0.f;
+            }
+            continue;
+        }
         float bv = -1.f;
         int bi = 0x7fffffff;
         for (int i = tid; i < C; i += blockDim.x)

@@ -145,6 +145,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// Prefetch of one tile into L2 only (no shared-memory destination, no completion signal): lets a single-buffered consumer spread
+// its HBM reads over a whole problem period and take the real load from L2 when its shared-memory slot frees up
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *m, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 // CTA-pair variant: executed by both CTAs of a pair; the data lands in the executing CTA's shared memory, the
 // complete_tx goes to the mbarrier of the pair's leader (even) CTA (peer bit 24 of the shared::cluster address cleared)
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1)
@@ -344,6 +352,35 @@ __device__ __forceinline__ float rcp_approx(float x)
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// ---------------------------------------------------------------- packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2)
+// Two independent IEEE-rounded f32 operations per instruction on a 64-bit register pair: same results as two scalar ops, one
+// issue slot (tools/microbench/chain_r02.cu: the packed forms issue every 2 clocks, i.e. they save issue bandwidth, not FLOPs).
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
 
 // ---------------------------------------------------------------- warp-level MMA (attention)

@@ -78,6 +78,7 @@ def lib():
         L.vitb200_test_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         L.vitb200_test_dequant.argtypes = [i32, vp, C.c_int64, vp]
         L.vitb200_test_attention.argtypes = [i32, i32, i32, i32, i32, vp, vp]
+        L.vitb200_test_attention_hilo.argtypes = [i32, i32, i32, i32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -155,13 +156,18 @@ def vit_predict(model: VitModel, images: np.ndarray, topk: int = 5, want_logits:
 
 
 def vit_predict_sharded(models, images: np.ndarray, topk: int = 5):
-    """Data-parallel batched vit_predict over several VitModel engines (one per GPU) from one host thread."""
+    """Data-parallel batched vit_predict over several VitModel engines (one per GPU) from one host thread.  Output shapes follow
+    vit_predict: a ViTSTR model (head_tokens = n) returns probs[B,n,C], topk[B,n,k]; all engines must hold the same model."""
     imgs = np.ascontiguousarray(images, dtype=np.float32)
     B = imgs.shape[0]
-    nc = models[0].num_classes
-    probs = np.empty((B, nc), np.float32)
-    idx = np.empty((B, topk), np.int32)
-    val = np.empty((B, topk), np.float32)
+    nc, ht = models[0].num_classes, models[0].head_tokens
+    if any(m.head_tokens != ht or m.num_classes != nc or m.in_chans != models[0].in_chans for m in models):
+        raise VitB200Error("vit_predict_sharded: the engines hold different models")
+    assert imgs.size == B * models[0].img_size * models[0].img_size * models[0].in_chans, imgs.shape
+    lead = (B,) if ht == 1 else (B, ht)
+    probs = np.empty(lead + (nc,), np.float32)
+    idx = np.empty(lead + (topk,), np.int32)
+    val = np.empty(lead + (topk,), np.float32)
     hs = (C.c_void_p * len(models))(*[m.handle for m in models])
     _check(lib().vitb200_forward_sharded(hs, len(models), imgs.ctypes.data, B, probs.ctypes.data, None, idx.ctypes.data,
                                          val.ctypes.data, topk), "vit_predict_sharded")
@@ -222,6 +228,23 @@ def test_attention(qkv16: np.ndarray, B: int, N: int, H: int, kernel: int = ATTN
     q = np.ascontiguousarray(qkv16, np.float16).reshape(B * N, 3 * H * 64)
     out = np.empty((B * N, H * 64), np.float32)
     _check(lib().vitb200_test_attention(device, kernel, B, N, H, q.ctypes.data, out.ctypes.data), "vitb200_test_attention")
+    return out
+
+
+def split_hi_lo(x: np.ndarray):
+    """x (float32) -> (hi, lo) float16 with hi = f16(x), lo = f16(x - hi): what the qkv GEMM's split-precision epilogue stores."""
+    x = np.ascontiguousarray(x, np.float32)
+    hi = x.astype(np.float16)
+    lo = (x - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def test_attention_hilo(qkv32: np.ndarray, B: int, N: int, H: int, device: int = 0) -> np.ndarray:
+    """The tcgen05 attention kernel (N <= 224) on split-precision operands: qkv32 float32 [B*N, 3*H*64] is passed as hi + lo."""
+    hi, lo = split_hi_lo(np.asarray(qkv32, np.float32).reshape(B * N, 3 * H * 64))
+    out = np.empty((B * N, H * 64), np.float32)
+    _check(lib().vitb200_test_attention_hilo(device, B, N, H, hi.ctypes.data, lo.ctypes.data, out.ctypes.data),
+           "vitb200_test_attention_hilo")
     return out
 
 
