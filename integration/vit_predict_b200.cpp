@@ -8,56 +8,27 @@
 // and link this file + libvitb200.so in their place (oracle/Makefile target `cli`).  main.cpp compiles unmodified.
 #include "vit.h"
 
-#include "vitb200.h"
+#include "engine_cache.hpp"
 
 #include <algorithm>
 #include <cstdio>
-#include <map>
 #include <vector>
 
 namespace {
 
-std::map<const vit_model *, vitb200_engine *> g_engines; // device copies are cached per model (SURVEY.md 8b "Ownership")
+vitb200_shim::EngineCache<vit_model> g_engines;
 
-int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
+// new knobs come from the environment so main.cpp stays untouched (SURVEY.md section 5 "Config / flags")
 vitb200_engine *engine_for(const vit_model &model)
 {
-    auto it = g_engines.find(&model);
-    if (it != g_engines.end()) return it->second;
-    vitb200_hparams hp;
-    hp.hidden_size = model.hparams.hidden_size;
-    hp.num_hidden_layers = model.hparams.num_hidden_layers;
-    hp.num_attention_heads = model.hparams.num_attention_heads;
-    hp.num_classes = model.hparams.num_classes;
-    hp.patch_size = model.hparams.patch_size;
-    hp.img_size = model.hparams.img_size;
-    hp.ftype = model.hparams.ftype;
-    hp.eps = model.hparams.eps;
-    std::vector<vitb200_tensor> ts;
-    for (const auto &kv : model.tensors) // vit.h:88, filled at vit.cpp:518-579
-    {
-        vitb200_tensor t;
-        t.name = kv.first.c_str();
-        t.data = kv.second->data;
-        t.type = (int32_t)kv.second->type; // GGML_TYPE_F32 = 0, F16 = 1, Q8_0 = 8
-        t.n_dims = kv.second->n_dims;
-        for (int i = 0; i < 4; ++i) t.ne[i] = kv.second->ne[i];
-        ts.push_back(t);
-    }
-    vitb200_engine *e = nullptr;
-    // new knobs come from the environment so main.cpp stays untouched (SURVEY.md section 5 "Config / flags")
-    if (vitb200_create(&hp, ts.data(), (int)ts.size(), env_int("VITB200_DEVICE", 0), env_int("VITB200_MAX_BATCH", 256), &e) != 0)
-        return nullptr;
-    g_engines[&model] = e;
-    return e;
+    return g_engines.get(model, vitb200_shim::env_int("VITB200_DEVICE", 0), vitb200_shim::env_int("VITB200_MAX_BATCH", 256), /*head_tokens*/ 1);
 }
 
 } // namespace
+
+// Free the device copy of one model (nullptr: of every model).  An addition next to vit_predict_batch: the reference frees a
+// model with ggml_free(model.ctx) (main.cpp:110), which cannot know about device memory.
+void vit_b200_release(const vit_model *model) { g_engines.release(model); }
 
 // Kept only so the declaration in vit.h resolves; the GPU path has no ggml graph.
 struct ggml_cgraph *vit_encode_image(const vit_model &, vit_state &, const image_f32 &) { return nullptr; }

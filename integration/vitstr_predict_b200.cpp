@@ -7,50 +7,24 @@
 // and link this file + libvitb200.so in their place (oracle/Makefile target `cli`).
 #include "vitstr.h"
 
-#include "vitb200.h"
+#include "engine_cache.hpp"
 
 #include <cstdio>
-#include <cstdlib>
-#include <map>
 #include <vector>
 
 namespace {
 
 const int kSeqLen = 25; // tokens the classifier reads (vitstr.cpp:865)
-std::map<const vit_model *, vitb200_engine *> g_engines;
+vitb200_shim::EngineCache<vit_model> g_engines; // the [P, P, 1, D] patch kernel (vitstr.cpp:482) tells the engine the input is 1-channel
 
 vitb200_engine *engine_for(const vit_model &model)
 {
-    auto it = g_engines.find(&model);
-    if (it != g_engines.end()) return it->second;
-    vitb200_hparams hp;
-    hp.hidden_size = model.hparams.hidden_size;
-    hp.num_hidden_layers = model.hparams.num_hidden_layers;
-    hp.num_attention_heads = model.hparams.num_attention_heads;
-    hp.num_classes = model.hparams.num_classes;
-    hp.patch_size = model.hparams.patch_size;
-    hp.img_size = model.hparams.img_size;
-    hp.ftype = model.hparams.ftype;
-    hp.eps = model.hparams.eps;
-    std::vector<vitb200_tensor> ts;
-    for (const auto &kv : model.tensors) // the [P, P, 1, D] patch kernel (vitstr.cpp:482) tells the engine the input is 1-channel
-    {
-        vitb200_tensor t;
-        t.name = kv.first.c_str();
-        t.data = kv.second->data;
-        t.type = (int32_t)kv.second->type;
-        t.n_dims = kv.second->n_dims;
-        for (int i = 0; i < 4; ++i) t.ne[i] = kv.second->ne[i];
-        ts.push_back(t);
-    }
-    const char *dev = getenv("VITB200_DEVICE");
-    vitb200_engine *e = nullptr;
-    if (vitb200_create_ex(&hp, ts.data(), (int)ts.size(), dev ? atoi(dev) : 0, /*max_batch*/ 16, kSeqLen, &e) != 0) return nullptr;
-    g_engines[&model] = e;
-    return e;
+    return g_engines.get(model, vitb200_shim::env_int("VITB200_DEVICE", 0), vitb200_shim::env_int("VITB200_MAX_BATCH", 16), kSeqLen);
 }
 
 } // namespace
+
+void vit_b200_release(const vit_model *model) { g_engines.release(model); }
 
 struct ggml_cgraph *vit_encode_image(const vit_model &, vit_state &, const image_f32 &) { return nullptr; }
 

@@ -3,12 +3,16 @@
  (2) the plain-C restatement (incl. per-layer taps), and (3) the compiled reference itself when oracle/_ref travelled.
 
 Tolerances: the north star asks for logits "within 1e-3 relative fp16 tolerance" and identical top-k.
- * max-norm error max|dlogit| / max|ref logit| and L2 error ||dlogits|| / ||ref logits||: two *correct*
-   implementations that are not bit-identical already differ by a median of 3e-4 (micro) / 6.5e-4 (tiny) / 7.8e-4 (base)
-   and up to 1.2e-3 (the oracle's own double-accumulation variant), and f16 Q/K/V add ~25 % (base
-   median 1.06e-3 in the same CPU experiment).  "<= 1e-3 on every image" is therefore not attainable by any
-   implementation on these weights; asserted: median over images <= 1.25e-3, every image <= 2e-3, L2 <= 1.5e-3.
- * top-5 identical wherever the reference's own top-5 logit gaps exceed 2.5x the observed error; |dp| <= 2e-3 absolute."""
+ * Metric: per image, max|dlogit| / max|ref logit|.  Two *correct* implementations that are not bit-identical
+   already differ by a median of 3e-4 (micro) / 6.4e-4 (tiny) / 7.6e-4 (base) and up to 1.2e-3 on single images: the restatement run
+   with double-precision accumulation and the reference's rounding points ("variant 1"; per-image values for the 64 headline images
+   are stored in tests/golden/base_f16_b64.npz as `floor`).  "<= 1e-3 on EVERY image" is therefore not attainable by any
+   implementation on these weights; what IS attainable, and asserted, is to sit AT that floor: the engine's error distribution must
+   stay within 1.1x of the floor distribution on the same images (median and 90th percentile), no image above 1.25e-3, and the
+   top-5 index lists must be identical with NO gap-aware exemption on the headline batch.
+ * Generic check (small fixtures of 2-12 images): median <= 1e-3, every image <= 1.25e-3 (1.5e-3 for the 2-layer-deep "micro"
+   models whose max|logit| is small), L2 <= 1.1e-3, top-5 identical wherever the reference's own top-5 logit gaps exceed 2.5x the
+   observed error (reported; 0 exemptions expected), |dp| no larger than the logit deviation allows."""
 import os
 
 import numpy as np
@@ -26,12 +30,12 @@ def rel_err(logits, ref_logits):
     return np.abs(logits - ref_logits).max(axis=1) / np.abs(ref_logits).max(axis=1)
 
 
-def check_parity(logits, probs, idx, ref_logits, ref_probs, k=5):
+def check_parity(logits, probs, idx, ref_logits, ref_probs, k=5, max_tol=1.25e-3):
     re = rel_err(logits, ref_logits)
     l2 = np.linalg.norm(logits - ref_logits, axis=1) / np.linalg.norm(ref_logits, axis=1)
-    assert l2.max() <= 1.5e-3, l2
-    assert np.median(re) <= 1.25e-3, re
-    assert re.max() <= 2e-3, re
+    assert l2.max() <= 1.1e-3 * (max_tol / 1.25e-3), l2
+    assert np.median(re) <= 1e-3, re
+    assert re.max() <= max_tol, re
     # probabilities: (a) exactly the soft-max of OUR logits (f32 rounding only); (b) against the reference no further off than
     # the logit deviation allows: |dp_i| = p_i |dl_i - sum_j p_j dl_j| <= 2 p_i (1 - p_i) max|dl| <= 0.5 max|dl| (first order)
     z = logits.astype(np.float64) - logits.max(axis=1, keepdims=True)
@@ -40,11 +44,15 @@ def check_parity(logits, probs, idx, ref_logits, ref_probs, k=5):
     dl = np.abs(logits - ref_logits).max(axis=1)
     assert (np.abs(probs - ref_probs).max(axis=1) <= 0.55 * dl + 1e-6).all(), (np.abs(probs - ref_probs).max(axis=1), dl)
     order = np.argsort(-ref_logits, 1)[:, : k + 1]
+    exempt = 0
     for b in range(logits.shape[0]):
         gaps = -np.diff(ref_logits[b, order[b]])
         err = np.abs(logits[b] - ref_logits[b]).max()
         if gaps.min() > 2.5 * err:  # otherwise a tie-flip is within the noise of ANY implementation
             assert (idx[b] == order[b, :k]).all(), (b, idx[b], order[b], gaps, err)
+        elif not (idx[b] == order[b, :k]).all():
+            exempt += 1
+    assert exempt <= max(1, logits.shape[0] // 16), f"{exempt} images needed the near-tie exemption"
     return re
 
 
@@ -54,7 +62,7 @@ def test_logits_and_topk_match_golden(cfg):
     m = eng.vit_model_load(model_path(cfg, "f16"), 0, 8)
     imgs = gf.synthetic_images(int(g["n_images"]), m.img_size, seed=int(g["image_seed"]))
     probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
-    check_parity(logits, probs, idx, g["logits"], g["probs"])
+    check_parity(logits, probs, idx, g["logits"], g["probs"], max_tol=1.5e-3 if cfg.startswith("micro") else 1.25e-3)
     # top-k values are the probabilities at those indices, descending
     assert np.array_equal(val, np.take_along_axis(probs, idx.astype(np.int64), 1))
     assert (np.diff(val, axis=1) <= 0).all()
@@ -111,25 +119,37 @@ def test_long_sequence_geometry_vit_large_384():
     m.close()
 
 
-@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not shipped")
-def test_full_depth_vit_large_384_bf16_weights_vs_live_reference():
+def test_full_depth_vit_large_384_bf16_weights_8_images():
     """BASELINE.json configs[2] at its real size (ViT-L/16-384: 24 layers, hidden 1024, 577 tokens, bf16-representable weights in
-    the f32 container): one image through the UNMODIFIED reference on the host cores against the engine, plus batch-position
-    invariance of the engine at a batch that makes every attention CTA loop over several heads."""
+    the f32 container): 8 seeded images against the UNMODIFIED reference's logits (tests/golden/large384_bf16w_b8.npz, generated
+    by tests/golden/make_golden_dist.py), per image, plus batch-position invariance at a batch that makes every attention CTA loop
+    over several heads.  The reference runs this file through its f32 path (f32 activations), the engine feeds f16 activations to
+    the tensor cores: the distance is the f16-activation noise of 24 layers (tiny, 12 layers: <= 2.5e-3), not an accumulation
+    artefact -- hence 4e-3 here instead of the f16 configs' 1.25e-3."""
+    g = np.load(os.path.join(GOLD, "large384_bf16w_b8.npz"))
+    n = int(g["n_images"])
     path = model_path("large384", "bf16w")
-    rm = ref.RefModel(path)
     m = eng.vit_model_load(path, 0, 12)
     imgs = gf.synthetic_images(12, m.img_size, seed=31)
-    p_ref, l_ref = rm.predict(imgs[5], n_threads=32)
-    rm.close()
+    fixed = gf.synthetic_images(n, m.img_size, seed=int(g["image_seed"]))
+    pos = [0, 1, 3, 5, 6, 8, 10, 11]
+    for j, p in enumerate(pos):
+        imgs[p] = fixed[j]
     probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
-    re = np.abs(logits[5] - l_ref).max() / np.abs(l_ref).max()
-    assert re <= 4e-3, re       # f16 activations vs the reference's f32 activations over 24 layers (tiny, 12 layers: <= 2.5e-3)
-    assert np.linalg.norm(logits[5] - l_ref) <= 2.5e-3 * np.linalg.norm(l_ref)
-    assert idx[5, 0] == l_ref.argmax()
+    re = rel_err(logits[pos], g["logits"])
+    l2 = np.linalg.norm(logits[pos] - g["logits"], axis=1) / np.linalg.norm(g["logits"], axis=1)
+    print("ViT-L/16-384 bf16w, 8 images vs reference: max-norm", re, "L2", l2)
+    assert re.max() <= 4e-3 and np.median(re) <= 3e-3, re
+    assert l2.max() <= 2.5e-3, l2
+    assert (idx[pos, 0] == g["logits"].argmax(1)).all()
     alone = eng.vit_predict(m, imgs[5:6], 5, want_logits=True)
     assert np.array_equal(alone[3][0], logits[5])
     assert np.isfinite(logits).all()
+    if ref.available():  # one image through the live reference on this host: the fixture is not stale
+        rm = ref.RefModel(path)
+        p_ref, l_ref = rm.predict(imgs[pos[2]], n_threads=32)
+        rm.close()
+        assert np.abs(l_ref - g["logits"][2]).max() <= 1e-6 * np.abs(l_ref).max()
     m.close()
 
 
@@ -164,25 +184,105 @@ def test_batch_invariance_and_ragged_batches():
     m.close()
 
 
-def test_full_batch_256_base_properties():
-    """BASELINE.json configs[1] size (ViT-B/16, batch 256): too slow for the CPU oracle on every image, so check
-    size-independent properties: duplicates of golden images placed anywhere in the batch reproduce the golden-parity
-    result bit-for-bit, probabilities sum to 1, top-k is sorted and consistent."""
-    g = np.load(os.path.join(GOLD, "base_f16.npz"))
+def test_full_batch_256_base_parity_at_the_noise_floor():
+    """BASELINE.json configs[1] at its real size (ViT-B/16, batch 256).  64 of the 256 images are the seeded fixtures of
+    tests/golden/base_f16_b64.npz (reference logits from the unmodified reference + per-image noise floor `floor`, the distance
+    of a correct-but-not-bit-identical CPU implementation on the same images); they are scattered over the batch (first / last
+    image, both sides of every 32-image boundary) and compared PER IMAGE:
+      * engine error distribution <= 1.1 x the floor distribution (median, 90th percentile), no image above 1.25e-3;
+      * top-5 index lists identical on all 64 images, no exemption; top-1 identical; |dp| bounded by the logit deviation;
+      * the same images alone (batch 64) give bit-identical logits (position / batch-mate invariance);
+      * size-independent properties on all 256: probabilities sum to 1, top-k sorted and consistent, everything finite."""
+    g = np.load(os.path.join(GOLD, "base_f16_b64.npz"))
+    n = int(g["n_images"])
     m = eng.vit_model_load(model_path("base", "f16"), 0, 256)
-    base = gf.synthetic_images(4, 224, seed=int(g["image_seed"]))
+    base = gf.synthetic_images(n, 224, seed=int(g["image_seed"]))
     imgs = gf.synthetic_images(256, 224, seed=99)
-    pos = [0, 127, 128, 255]
+    pos = sorted(set([0, 255] + list(range(31, 256, 32)) + list(range(32, 256, 32)) + list(range(3, 256, 5))))[:n]
+    assert len(pos) == n
     for j, p in enumerate(pos):
         imgs[p] = base[j]
     probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
-    check_parity(logits[pos], probs[pos], idx[pos], g["logits"], g["probs"])
+    re = rel_err(logits[pos], g["logits"])
+    floor = g["floor"]
+    stats = dict(median=float(np.median(re)), p90=float(np.quantile(re, 0.9)), max=float(re.max()),
+                 floor_median=float(np.median(floor)), floor_p90=float(np.quantile(floor, 0.9)), floor_max=float(floor.max()))
+    print("base f16 B=256, 64 images vs reference:", stats)
+    assert np.median(re) <= 1.1 * np.median(floor), stats
+    assert np.quantile(re, 0.9) <= 1.1 * np.quantile(floor, 0.9), stats
+    assert re.max() <= 1.25e-3, stats
+    order = np.argsort(-g["logits"], 1)[:, :5]
+    assert (order == idx[pos]).all(), np.nonzero((order != idx[pos]).any(1))   # all 64 top-5 lists, no exemption
+    dl = np.abs(logits[pos] - g["logits"]).max(axis=1)
+    assert (np.abs(probs[pos] - g["probs"]).max(axis=1) <= 0.55 * dl + 1e-6).all()
     small = eng.vit_predict(m, base, 5, want_logits=True)
     assert np.array_equal(small[3], logits[pos])
     np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-3)
     assert (np.diff(val, axis=1) <= 0).all()
     assert np.array_equal(idx[:, 0], probs.argmax(1))
     assert np.isfinite(logits).all()
+    m.close()
+
+
+def test_loader_rejects_wrong_shapes_and_duplicate_names():
+    """The reference loader compares all four extents of every tensor with the model's declaration (vit.cpp:633-641, "has wrong
+    shape in model file") and keeps tensors in a name-keyed map; vitb200_create must do the same instead of accepting any tensor
+    with the right element count: a transposed square weight would load silently and produce garbage."""
+    vf = gf.read(model_path("micro", "f16"))
+
+    def transpose_proj(entries):
+        for e in entries:
+            if e[0] == "blocks.0.attn.qkv.weight":
+                e[3] = [e[3][1], e[3][0]]      # [3D, D] instead of [D, 3D]: same element count
+    with pytest.raises(eng.VitB200Error) as ei:
+        eng.vit_model_from_tensors(vf, edit=transpose_proj)
+    assert "wrong shape" in str(ei.value) and "blocks.0.attn.qkv.weight" in str(ei.value)
+
+    def flat_pos(entries):
+        for e in entries:
+            if e[0] == "pos_embed":
+                e[3] = [int(np.prod(e[3]))]    # 1-D with the right count
+    with pytest.raises(eng.VitB200Error) as ei:
+        eng.vit_model_from_tensors(vf, edit=flat_pos)
+    assert "wrong shape" in str(ei.value)
+
+    def duplicate(entries):
+        return entries + [entries[5]]
+    with pytest.raises(eng.VitB200Error) as ei:
+        eng.vit_model_from_tensors(vf, edit=duplicate)
+    assert "duplicate tensor" in str(ei.value)
+
+    # and the untouched list loads and matches the file path bit for bit
+    m1 = eng.vit_model_from_tensors(vf, max_batch=2)
+    m2 = eng.vit_model_load(model_path("micro", "f16"), 0, 2)
+    imgs = gf.synthetic_images(2, vf.img_size, seed=3)
+    assert np.array_equal(eng.vit_predict(m1, imgs, 5, want_logits=True)[3], eng.vit_predict(m2, imgs, 5, want_logits=True)[3])
+    m1.close()
+    m2.close()
+
+
+@pytest.mark.parametrize("classes", [10, 1001, 21843])
+def test_class_counts_that_are_not_a_multiple_of_four(classes, tmp_path):
+    """ImageNet-21k heads have 21843 classes (the reference runs them); the head GEMM pads the class count to a multiple of 4
+    internally (zero weight rows through TMA out-of-bounds fill, zero bias) and every output stays dense [batch][num_classes].
+    21843 floats also exceed the 48 KB default of the soft-max kernel's dynamic shared memory (opt-in up to 227 KB)."""
+    path = str(tmp_path / f"micro-c{classes}.gguf")
+    gf.write_synthetic(path, "micro", 1, classes=classes, seed=5)
+    vf = gf.read(path)
+    om = rs.OracleModel(vf, gf.tensor_specs)
+    imgs = gf.synthetic_images(3, vf.img_size, seed=9)
+    m = eng.vit_model_load(path, 0, 4)
+    probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
+    assert probs.shape == (3, classes) and logits.shape == (3, classes)
+    p_ref, l_ref = om.forward_batch(imgs)
+    assert rel_err(logits, l_ref).max() <= 1.5e-3
+    assert (idx[:, 0] == l_ref.argmax(1)).all()
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-3)
+    assert np.abs(probs - p_ref).max() <= 1e-3
+    # k larger than the class count is clamped: the tail is (-1, 0)
+    if classes == 10:
+        p2, i2, v2 = eng.vit_predict(m, imgs, 12)
+        assert (i2[:, 10:] == -1).all() and (v2[:, 10:] == 0).all() and (np.sort(i2[:, :10], 1) == np.arange(10)).all()
     m.close()
 
 
@@ -212,7 +312,9 @@ def test_quantised_model_file_top_k_and_noise_floor(cfg, fmt):
     imgs = gf.synthetic_images(int(g["n_images"]), m.img_size, seed=int(g["image_seed"]))
     probs, idx, val, logits = eng.vit_predict(m, imgs, 5, want_logits=True)
     re = rel_err(logits, g["logits"])
-    assert re.max() <= 4e-2, re
+    # measured floor of ANY dequantised-weight x f16-activation implementation against the reference's integer dot (CPU, restatement
+    # on the dequantised weights): 1.0e-2 .. 2.0e-2; q8_0 (the BASELINE config) sits at the low end
+    assert re.max() <= (2.5e-2 if fmt == "q8_0" else 3.5e-2), re
     order = np.argsort(-g["logits"], 1)
     for b in range(imgs.shape[0]):
         gaps = -np.diff(g["logits"][b, order[b, :6]])
@@ -305,7 +407,7 @@ def test_forward_u8_end_to_end_vs_reference_pipeline():
     f32, probs, idx, val, logits = eng.vit_image_preprocess_predict(m, imgs, topk=5)
     for b, im in enumerate(imgs):
         p_ref, l_ref = rm.predict(rm.preprocess(im), n_threads=8)
-        assert np.abs(logits[b] - l_ref).max() <= 2e-3 * np.abs(l_ref).max()
+        assert np.abs(logits[b] - l_ref).max() <= 1.25e-3 * np.abs(l_ref).max()
         assert idx[b, 0] == l_ref.argmax()
     m.close()
     rm.close()
@@ -373,8 +475,8 @@ def test_vitstr_extension_matches_the_reference(cfg):
     assert logits.shape == (n, 25, m.num_classes) and idx.shape == (n, 25, 5)
     lf, rf = logits.reshape(n, -1), g["logits"].reshape(n, -1)
     re = np.abs(lf - rf).max(1) / np.abs(rf).max(1)
-    assert np.median(re) <= 1.25e-3 and re.max() <= 2e-3, re
-    assert (np.linalg.norm(lf - rf, axis=1) <= 1.5e-3 * np.linalg.norm(rf, axis=1)).all()
+    assert np.median(re) <= 1e-3 and re.max() <= 1.5e-3, re
+    assert (np.linalg.norm(lf - rf, axis=1) <= 1.25e-3 * np.linalg.norm(rf, axis=1)).all()
     # greedy decode = per-token argmax (vitstr.cpp:1029-1052): identical wherever the reference's top-2 gap exceeds the error
     top2 = np.sort(g["logits"], -1)[..., -2:]
     clear = (top2[..., 1] - top2[..., 0]) > 2.5 * np.abs(logits - g["logits"]).max(-1)
@@ -387,7 +489,7 @@ def test_vitstr_extension_matches_the_reference(cfg):
         extra = gf.synthetic_gray_images(1, m.img_size, seed=77)
         p_ref, l_ref = rm.predict(extra[0], n_threads=8)
         got = eng.vit_predict(m, extra, 5, want_logits=True)[3][0]
-        assert np.abs(got - l_ref).max() <= 2e-3 * np.abs(l_ref).max()
+        assert np.abs(got - l_ref).max() <= 1.5e-3 * np.abs(l_ref).max()
         rm.close()
     # a 3-channel classifier entry point must refuse this model's input
     with pytest.raises(eng.VitB200Error):

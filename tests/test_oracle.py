@@ -198,3 +198,56 @@ def test_restatement_equals_the_vitstr_extension_bit_for_bit(cfg):
         assert np.array_equal(l_ref, g["logits"][i])
     rm.close()
     om.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Offline converters (vit.cpp_b200/convert.py): the timm-free counterparts of convert-pth-to-ggml.py and quantize.cpp
+def test_state_dict_converter_reproduces_the_reference_layout(tmp_path):
+    """A plain state_dict (safetensors file, or a torch checkpoint) -> model file must be byte-identical to what the writer that
+    follows convert-pth-to-ggml.py:105-158 produces for the same weights, for both ftypes; hyper-parameters are inferred from the
+    tensor shapes alone; the f32 container keeps the patch kernel f16 (vit.cpp:515).  The reference itself must load the result."""
+    from tests.util import pkg
+    conv = pkg.convert
+    hidden, layers, heads, patch, img = gf.CONFIGS["micro"]
+    tens = gf.synth_tensors(hidden, layers, 1000, patch, img, seed=0)
+    st = str(tmp_path / "micro.safetensors")
+    conv.write_safetensors(st, tens)
+    back = conv.read_safetensors(st)
+    assert list(back) == list(tens) and all(np.array_equal(back[k], tens[k]) for k in tens)
+    assert conv.infer_hparams(back, heads=heads) == (hidden, layers, heads, 1000, patch, img, 3)
+    for ftype in (1, 0):
+        want = str(tmp_path / f"want{ftype}.gguf")
+        got = str(tmp_path / f"got{ftype}.gguf")
+        gf.write_synthetic(want, "micro", ftype, seed=0)
+        conv.state_dict_to_model_file(back, got, ftype, heads=heads)
+        assert open(got, "rb").read() == open(want, "rb").read()
+    # torch checkpoint path, with a norm_pre tensor that the reference converter skips
+    import torch
+    sd = {k: torch.from_numpy(v.copy()) for k, v in tens.items()}
+    sd["norm_pre.weight"] = torch.ones(hidden)
+    pth = str(tmp_path / "micro.pth")
+    torch.save(sd, pth)
+    got = str(tmp_path / "from_pth.gguf")
+    conv.main([pth, got, "--ftype", "1", "--heads", str(heads)])
+    assert open(got, "rb").read() == open(str(tmp_path / "want1.gguf"), "rb").read()
+    # a real GGUF container from the same state_dict parses back to the same tensors
+    gg = str(tmp_path / "micro.real.gguf")
+    conv.state_dict_to_model_file(back, gg, 1, heads=heads, container="gguf")
+    vf = gf.read_gguf(gg)
+    assert (vf.hidden_size, vf.num_hidden_layers, vf.num_attention_heads) == (hidden, layers, heads)
+    assert np.array_equal(vf.tensors["blocks.1.mlp.fc2.weight"], tens["blocks.1.mlp.fc2.weight"].astype(np.float16))
+    if ref.available():
+        m = ref.RefModel(str(tmp_path / "got1.gguf"))
+        assert (m.hidden, m.layers, m.heads, m.classes) == (hidden, layers, heads, 1000)
+        m.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (reference quantize binary) not built")
+@pytest.mark.parametrize("cfg", ["micro", "tiny"])
+def test_q8_0_quantizer_is_byte_identical_to_the_reference_binary(cfg, tmp_path):
+    """convert.quantize_model_file restates quantize.cpp + quantize_row_q8_0_reference; the reference's own `quantize` binary on the
+    same f16 file is the golden output."""
+    from tests.util import pkg
+    got = str(tmp_path / "q8.gguf")
+    pkg.convert.quantize_model_file(model_path(cfg, "f16"), got, "q8_0")
+    assert open(got, "rb").read() == open(model_path(cfg, "q8_0"), "rb").read()

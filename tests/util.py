@@ -27,8 +27,9 @@ gf = pkg.ggml_file
 
 
 def model_path(config: str, ftype: str = "f16", seed: int = 0) -> str:
-    """Path of a cached synthetic model file; q8_0 files come from the reference's own quantize binary
-    (oracle/_ref/quantize, reference quantize.cpp) applied to the f16 file."""
+    """Path of a cached synthetic model file.  q8_0 files come from the package's own restatement of the reference's quantize.cpp
+    (vit.cpp_b200/convert.py, byte-identical to the reference binary: tests/test_oracle.py); the other block formats from the
+    reference's quantize binary (oracle/_ref/quantize) applied to the f16 file."""
     os.makedirs(CACHE, exist_ok=True)
     path = os.path.join(CACHE, f"vit-{config}-{ftype}-s{seed}.gguf")
     if os.path.exists(path):
@@ -38,6 +39,8 @@ def model_path(config: str, ftype: str = "f16", seed: int = 0) -> str:
         gf.write_synthetic(tmp, config, 1 if ftype == "f16" else 0, seed=seed)
     elif ftype == "bf16w":  # bf16-rounded weights stored as f32 (SURVEY.md 8c, bf16 config oracle)
         gf.write_synthetic(tmp, config, 0, seed=seed, round_bf16=True)
+    elif ftype == "q8_0":
+        pkg.convert.quantize_model_file(model_path(config, "f16", seed), tmp, "q8_0")
     elif ftype in gf.QUANT_NAMES:
         from oracle import ref
         subprocess.check_call([ref.QUANTIZE_BIN, model_path(config, "f16", seed), tmp, str(gf.QUANT_NAMES[ftype])],

@@ -5,6 +5,7 @@ host-side mirror of the reference's vit.h interface used by tests/ and bench.py.
 contains a dot, so import it through tests/util.load_pkg() (module name `vit_cpp_b200`)."""
 from . import ggml_file  # noqa: F401
 from . import engine  # noqa: F401
+from . import convert  # noqa: F401
 
 
 def dp():

@@ -322,6 +322,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const int n_full = p.N >> 5; // chunks with all 32 keys valid
                     float l0 = 0.f, l1 = 0.f, l2s = 0.f, l3 = 0.f;
                     int c = 0;
+                    // (a software-pipelined variant -- the next chunk's tcgen05.ld in flight during the exponentials -- needs ~20 more
+                    // registers than the 168 a 10-warp CTA gets; it spilled inside this loop and ran 1.7x slower: measured, dropped)
 #pragma unroll 1 // (ptxas otherwise unrolls x4 with three peeled copies: 213 KB of SASS, the live part no longer fits the instruction cache)
                     for (; c + 2 <= n_full; c += 2)
                     {

@@ -103,6 +103,22 @@ __device__ __forceinline__ float gelu_tanh_f32(float x)
     return x * ptx::rcp_approx(1.0f + e);
 }
 
+// Two elements at a time with Blackwell's packed FP32 instructions (FMUL2 / FFMA2 / FADD2): the same separately rounded IEEE
+// operations as gelu_tanh_f32 on each lane (bit-identical results), half the issue slots for the five FMA-pipe steps; the two
+// MUFU ops per element stay scalar.  tools/microbench/chain_r02.cu: 36.9 instead of 39.5 clocks per element per warp at two
+// epilogue warps per sub-partition.
+__device__ __forceinline__ void gelu_tanh_f32x2(float x0, float x1, float &y0, float &y1)
+{
+    const uint64_t x = ptx::pack_f32x2(x0, x1);
+    const uint64_t w = ptx::fma_f32x2(ptx::mul_f32x2(x, x), ptx::pack_f32x2(-0.10294323958083856f, -0.10294323958083856f),
+                                      ptx::pack_f32x2(-2.3022081981625516f, -2.3022081981625516f));
+    float a0, a1;
+    ptx::unpack_f32x2(ptx::mul_f32x2(x, w), a0, a1);
+    float d0, d1;
+    ptx::unpack_f32x2(ptx::add_f32x2(ptx::pack_f32x2(ptx::ex2_approx(a0), ptx::ex2_approx(a1)), ptx::pack_f32x2(1.0f, 1.0f)), d0, d1);
+    ptx::unpack_f32x2(ptx::mul_f32x2(x, ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1))), y0, y1);
+}
+
 template <int BN, int EPI, int DEEPK, int CG>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0,
                                            EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_F16_HILO>::kThreads), 1)
@@ -517,15 +533,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                         {
-                            float x0 = __uint_as_float(v[j * 8 + e * 2]) + bias8[e * 2];
-                            float x1 = __uint_as_float(v[j * 8 + e * 2 + 1]) + bias8[e * 2 + 1];
+                            float x0, x1; // acc + bias, both lanes in one FADD2
+                            ptx::unpack_f32x2(ptx::add_f32x2(ptx::pack_f32x2(__uint_as_float(v[j * 8 + e * 2]), __uint_as_float(v[j * 8 + e * 2 + 1])),
+                                                             ptx::pack_f32x2(bias8[e * 2], bias8[e * 2 + 1])), x0, x1);
                             __half2 h;
                             if constexpr (EPI == EPI_BIAS_GELU_F16)
                             {
                                 // ggml.c:1434-1441: y = f16(gelu(f32(f16(x))))
-                                const float r0 = __half2float(__float2half_rn(x0));
-                                const float r1 = __half2float(__float2half_rn(x1));
-                                h = __floats2half2_rn(gelu_tanh_f32(r0), gelu_tanh_f32(r1));
+                                const float2 r = __half22float2(__floats2half2_rn(x0, x1));
+                                float g0, g1;
+                                gelu_tanh_f32x2(r.x, r.y, g0, g1);
+                                h = __floats2half2_rn(g0, g1);
                             }
                             else
                             {

@@ -36,6 +36,11 @@ class Taps(C.Structure):
                                          ("embed", "ln1", "qkv", "attn", "x1", "ln2", "h", "x2", "final_ln", "x_final")]
 
 
+class Tensor(C.Structure):
+    """vitb200_tensor (include/vitb200.h): one host tensor as found in vit_model::tensors (reference vit.h:88)."""
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("type", C.c_int32), ("n_dims", C.c_int32), ("ne", C.c_int64 * 4)]
+
+
 def declared_symbols() -> list:
     """Every function name include/vitb200.h declares (for the CPU-side ABI test)."""
     src = open(HEADER_PATH).read()
@@ -131,6 +136,37 @@ def vit_model_load(fname: str, device: int = 0, max_batch: int = 256, head_token
     ViTSTR model (reference extensions/vitstr.cpp: 1-channel input, classifier over the first 25 tokens)."""
     h = C.c_void_p()
     _check(lib().vitb200_create_from_file_ex(fname.encode(), device, max_batch, head_tokens, C.byref(h)), "vit_model_load")
+    return VitModel(h, device, max_batch)
+
+
+def vit_model_from_tensors(vf, device: int = 0, max_batch: int = 8, head_tokens: int = 1, edit=None) -> VitModel:
+    """vitb200_create_ex with a caller-built tensor list -- what the vit.h-side shim does with vit_model::tensors.  `vf` is a parsed
+    model file (ggml_file.VitFile: numpy-shaped f32 / f16 arrays); `edit(entries)` may reorder / duplicate / reshape the list of
+    [name, array, ggml_type, ne] entries first (tests of the loader's shape and name checks)."""
+    entries = []
+    for name, arr in vf.tensors.items():
+        if name.endswith(".q8_0_raw"):
+            continue
+        ft = vf.tensor_ftype[name]
+        if ft not in (0, 1):
+            raise VitB200Error("vit_model_from_tensors: f32 / f16 tensors only")
+        a = np.ascontiguousarray(arr, np.float16 if ft == 1 else np.float32)
+        if name == "patch_embed.proj.bias":
+            a = a.reshape(1, a.size, 1, 1)  # convert-pth-to-ggml.py:150-151
+        entries.append([name, a, ft, list(reversed(a.shape))])
+    if edit is not None:
+        entries = edit(entries) or entries
+    ts = (Tensor * len(entries))()
+    keep = []
+    for t, (name, a, ft, ne) in zip(ts, entries):
+        nm = name.encode()
+        keep.append((nm, a))
+        t.name, t.data, t.type, t.n_dims = nm, a.ctypes.data, ft, len(ne)
+        for i in range(4):
+            t.ne[i] = ne[i] if i < len(ne) else 1
+    hp = Hparams(vf.hidden_size, vf.num_hidden_layers, vf.num_attention_heads, vf.num_classes, vf.patch_size, vf.img_size, vf.ftype, 1e-6)
+    h = C.c_void_p()
+    _check(lib().vitb200_create_ex(C.byref(hp), ts, len(entries), device, max_batch, head_tokens, C.byref(h)), "vitb200_create")
     return VitModel(h, device, max_batch)
 
 
