@@ -156,10 +156,15 @@ struct vitb200_engine
     int32_t *d_topk_idx = nullptr;
     __half *A16 = nullptr, *QKV16 = nullptr, *H16 = nullptr, *CLS16 = nullptr, *PA = nullptr;
     __half *QKV16L = nullptr; // lo halves of q, k, v (x - f16(x), as f16): the tcgen05 attention's split-precision operands
+    int *d_ln_count = nullptr; // fused LayerNorm: one completion counter per 32-row group of the residual stream (zero between launches)
+    bool fused_ln = false;     // LayerNorm applied inside the proj / fc2 residual epilogues (VITB200_FUSED_LN=0: separate kernel)
     bool attn_hilo = false;   // qkv GEMM emits hi + lo and attention_tc_kernel runs the 3 + 2 term products (VITB200_ATTN_HILO=0: hi only)
     CUtensorMap tmQl, tmKVl;
-    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmX, tmQ, tmKV, tmAO, tmKV64;
-    std::map<int, CUtensorMap> tmX_batch; // residual-stream map clipped to batch * N rows: TMA neither loads nor stores rows past the batch
+    CUtensorMap tmA_D, tmA_H, tmA_P, tmA_C, tmQ, tmKV, tmAO, tmKV64;
+    // maps of the tensors the GEMM epilogues WRITE with TMA, clipped to batch * N rows so that nothing past the batch is ever
+    // stored (and, for the residual stream, loaded): X f32 (32 x 32 boxes), QKV hi / lo and the MLP hidden buffer f16 (64 x 32 boxes)
+    struct BatchMaps { CUtensorMap X, QKVh, QKVl, H; };
+    std::map<int, BatchMaps> batch_maps;
     bool attn_tc = false;      // tcgen05 single-block attention (N <= 224)
     bool attn_tc_long = false; // tcgen05 two-sweep attention (224 < N <= 640); anything longer uses the mma.sync two-pass kernel
     int max_k = 16;
@@ -435,7 +440,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 template <int BN, int EPI, int CG, int DEEPK = 0>
-int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
+int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const CUtensorMap &tmO2, const GemmParams &p, cudaStream_t s, int num_sms)
 {
     using Cfg = GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0,
                         EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_F16_HILO>;
@@ -465,25 +470,26 @@ int launch_gemm_t(vitb200_engine *e, const CUtensorMap &tmA, const CUtensorMap &
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmX, p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmX, tmO2, p));
     if (e) e->launches++;
     return 0;
 }
 
-// tmB: box rows = bn / cg.  tmX: f32 [M][ldo] map of the residual/output (EPI_BIAS_RESID_F32 only; ignored otherwise)
-int launch_gemm(vitb200_engine *e, int cg, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const GemmParams &p, cudaStream_t s, int num_sms)
+// tmB: box rows = bn / cg.  tmX: EPI_BIAS_RESID_F32 -- f32 [M][ldo] map of the residual/output; f16 epilogues -- f16 [M][ldo] map of the
+// output (64 x 32 boxes) and tmO2 the lo tensor of EPI_BIAS_F16_HILO; ignored otherwise
+int launch_gemm(vitb200_engine *e, int cg, int bn, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmX, const CUtensorMap &tmO2, const GemmParams &p, cudaStream_t s, int num_sms)
 {
 #define VB_CASE(BN, EPI)                                                                                         \
     if (bn == BN && epi == EPI)                                                                                  \
-        return cg == 2 ? launch_gemm_t<BN, EPI, 2>(e, tmA, tmB, tmX, p, s, num_sms) : launch_gemm_t<BN, EPI, 1>(e, tmA, tmB, tmX, p, s, num_sms);
+        return cg == 2 ? launch_gemm_t<BN, EPI, 2>(e, tmA, tmB, tmX, tmO2, p, s, num_sms) : launch_gemm_t<BN, EPI, 1>(e, tmA, tmB, tmX, tmO2, p, s, num_sms);
     if (epi == EPI_PATCH_GATHER_F32) // CTA pairs only (the A producers fill three pipeline stages at a time)
     {
         if (cg != 2) return fail("gathered patch embedding needs cta_group 2");
-        return bn == 256 ? launch_gemm_t<256, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, p, s, num_sms)
-                         : launch_gemm_t<128, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, p, s, num_sms);
+        return bn == 256 ? launch_gemm_t<256, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, tmO2, p, s, num_sms)
+                         : launch_gemm_t<128, EPI_PATCH_GATHER_F32, 2>(e, tmA, tmB, tmX, tmO2, p, s, num_sms);
     }
     if (epi == EPI_BIAS_RESID_F32 && bn == 256 && cg == 2 && p.K >= 2048) // fc2: shallower residual ring, one more operand stage
-        return launch_gemm_t<256, EPI_BIAS_RESID_F32, 2, 1>(e, tmA, tmB, tmX, p, s, num_sms);
+        return launch_gemm_t<256, EPI_BIAS_RESID_F32, 2, 1>(e, tmA, tmB, tmX, tmO2, p, s, num_sms);
     VB_CASE(256, EPI_BIAS_F16) VB_CASE(128, EPI_BIAS_F16)
     VB_CASE(256, EPI_BIAS_F16_HILO) VB_CASE(128, EPI_BIAS_F16_HILO)
     VB_CASE(256, EPI_BIAS_GELU_F16) VB_CASE(128, EPI_BIAS_GELU_F16)
@@ -685,19 +691,21 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     const int D = e->hp.hidden_size, N = e->N, T = B * N, C = e->hp.num_classes;
     e->launches = 0;
     __half *PA = e->PA;
-    // the residual epilogue read-modify-writes whole 32-row boxes of X: with a map of exactly T rows the rows of the last M tile
-    // that lie past the batch are zero-filled on load and clipped on store, so nothing outside the batch is ever written
-    if (B != e->max_batch)
+    // the epilogues store whole boxes with TMA (and the residual epilogue read-modify-writes 32-row boxes of X): with maps of exactly T
+    // rows the rows of the last M tile that lie past the batch are zero-filled on load and clipped on store
+    auto bm = e->batch_maps.find(B);
+    if (bm == e->batch_maps.end())
     {
-        auto it = e->tmX_batch.find(B);
-        if (it == e->tmX_batch.end())
-        {
-            CUtensorMap m;
-            if (make_tmap_f32_box32(&m, e->X, (uint64_t)T, (uint64_t)D, (uint64_t)D)) return 1;
-            it = e->tmX_batch.emplace(B, m).first;
-        }
+        vitb200_engine::BatchMaps m;
+        memset(&m, 0, sizeof(m));
+        if (make_tmap_f32_box32(&m.X, e->X, (uint64_t)T, (uint64_t)D, (uint64_t)D) ||
+            make_tmap(&m.QKVh, e->QKV16, (uint64_t)T, 3 * (uint64_t)D, 3 * (uint64_t)D, 32) ||
+            (e->QKV16L && make_tmap(&m.QKVl, e->QKV16L, (uint64_t)T, 3 * (uint64_t)D, 3 * (uint64_t)D, 32)) ||
+            make_tmap(&m.H, e->H16, (uint64_t)T, 4 * (uint64_t)D, 4 * (uint64_t)D, 32))
+            return 1;
+        bm = e->batch_maps.emplace(B, m).first;
     }
-    const CUtensorMap &tmX = B == e->max_batch ? e->tmX : e->tmX_batch.find(B)->second;
+    const CUtensorMap &tmX = bm->second.X, &tmQKVh = bm->second.QKVh, &tmQKVl = bm->second.QKVl, &tmH = bm->second.H;
 
     // patch embedding (vit.cpp:772-797).  P = 16 with CTA pairs: ONE kernel -- the GEMM's A producers gather the f32 pixels
     // straight into the tcgen05 operand tiles (no im2col buffer) and the epilogue adds conv bias + pos_embed and writes token
@@ -716,24 +724,28 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         p.pos = e->pos; p.np = e->NP; p.ntok = N;
         p.img = d_images; p.S = e->hp.img_size; p.G = e->G;
         ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
-        if (launch_gemm(e, e->cta_group, e->patch.bn, fused_patch ? EPI_PATCH_GATHER_F32 : EPI_PATCH_F32, e->tmA_P, e->patch.tm, tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->patch.bn, fused_patch ? EPI_PATCH_GATHER_F32 : EPI_PATCH_F32, e->tmA_P, e->patch.tm, tmX, tmX, p, s, e->num_sms)) return 1;
     }
     if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
 
-    for (int il = 0; il < e->hp.num_hidden_layers; ++il)
+    const int n_layers = e->hp.num_hidden_layers;
+    for (int il = 0; il < n_layers; ++il)
     {
         const Layer &L = e->layers[il];
         const bool tap = taps && taps->layer == il;
+        // LayerNorm 1 (vit.cpp:808-812): a kernel of its own only in front of the first block -- with fused_ln the fc2 epilogue of
+        // the previous block has already left norm1(x) of this block in A16
+        if (il == 0 || !e->fused_ln)
         {
             ProfScope ps(e, PK_LN, 0.0, s);
-            if (launch_layernorm(e, e->X, (size_t)D, L.n1w, L.n1b, e->A16, T, s)) return 1; // vit.cpp:808-812
+            if (launch_layernorm(e, e->X, (size_t)D, L.n1w, L.n1b, e->A16, T, s)) return 1;
+            if (tap && tap_f16(taps->ln1, e->A16, (size_t)T * D, s)) return 1;
         }
-        if (tap && tap_f16(taps->ln1, e->A16, (size_t)T * D, s)) return 1;
         {
             GemmParams p{};
             p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.out2 = e->QKV16L; p.ldo = 3 * D;
             ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.qkv.bn, e->attn_hilo ? EPI_BIAS_F16_HILO : EPI_BIAS_F16, e->tmA_D, L.qkv.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:820-821
+            if (launch_gemm(e, e->cta_group, L.qkv.bn, e->attn_hilo ? EPI_BIAS_F16_HILO : EPI_BIAS_F16, e->tmA_D, L.qkv.tm, tmQKVh, tmQKVl, p, s, e->num_sms)) return 1; // vit.cpp:820-821
         }
         if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s, e->attn_hilo ? e->QKV16L : nullptr)) return 1;
         {
@@ -742,12 +754,16 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         }
         if (tap && tap_f16(taps->attn, e->A16, (size_t)T * D, s)) return 1;
         {
+            // proj + residual (vit.cpp:868-873); fused: + LayerNorm 2 (vit.cpp:881-885) of each 32-row group as its last column tile
+            // lands, written over the attention output in A16 (every tile that read those rows has finished its MMAs by then)
             GemmParams p{};
             p.M = T; p.N = D; p.K = D; p.bias = L.proj.b; p.out = e->X; p.ldo = D; p.resid = e->X;
+            if (e->fused_ln) { p.ln_out = e->A16; p.ln_w = L.n2w; p.ln_b = L.n2b; p.ln_count = e->d_ln_count; p.ln_eps = e->hp.eps; p.ln_dbg = getenv("VITB200_LN_DBG") ? atoi(getenv("VITB200_LN_DBG")) : 0; }
             ProfScope ps(e, PK_PROJ, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:868-873
+            if (launch_gemm(e, e->cta_group, L.proj.bn, EPI_BIAS_RESID_F32, e->tmA_D, L.proj.tm, tmX, tmX, p, s, e->num_sms)) return 1;
         }
         if (tap && tap_f32(taps->x1, e->X, (size_t)T * D, s)) return 1;
+        if (!e->fused_ln)
         {
             ProfScope ps(e, PK_LN, 0.0, s);
             if (launch_layernorm(e, e->X, (size_t)D, L.n2w, L.n2b, e->A16, T, s)) return 1; // vit.cpp:881-885
@@ -757,16 +773,25 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
             GemmParams p{};
             p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D;
             ProfScope ps(e, PK_FC1, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:889-893
+            if (launch_gemm(e, e->cta_group, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, tmH, tmH, p, s, e->num_sms)) return 1; // vit.cpp:889-893
         }
         if (tap && tap_f16(taps->h, e->H16, (size_t)T * 4 * D, s)) return 1;
         {
+            // fc2 + residual (vit.cpp:896-900); fused: + LayerNorm 1 of the NEXT block (the last block's output goes to the pooled
+            // final LayerNorm instead)
             GemmParams p{};
             p.M = T; p.N = D; p.K = 4 * D; p.bias = L.fc2.b; p.out = e->X; p.ldo = D; p.resid = e->X;
+            if (e->fused_ln && il + 1 < n_layers)
+            {
+                const Layer &Ln = e->layers[il + 1];
+                p.ln_out = e->A16; p.ln_w = Ln.n1w; p.ln_b = Ln.n1b; p.ln_count = e->d_ln_count; p.ln_eps = e->hp.eps;
+                p.ln_dbg = getenv("VITB200_LN_DBG") ? atoi(getenv("VITB200_LN_DBG")) : 0;
+            }
             ProfScope ps(e, PK_FC2, 2.0 * p.M * p.N * p.K, s);
-            if (launch_gemm(e, e->cta_group, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, tmX, p, s, e->num_sms)) return 1; // vit.cpp:896-900
+            if (launch_gemm(e, e->cta_group, L.fc2.bn, EPI_BIAS_RESID_F32, e->tmA_H, L.fc2.tm, tmX, tmX, p, s, e->num_sms)) return 1;
         }
         if (tap && tap_f32(taps->x2, e->X, (size_t)T * D, s)) return 1;
+        if (e->fused_ln && taps && taps->layer == il + 1 && tap_f16(taps->ln1, e->A16, (size_t)T * D, s)) return 1; // norm1 of the next block
     }
     if (taps && tap_f32(taps->x_final, e->X, (size_t)T * D, s)) return 1;
 
@@ -783,7 +808,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         GemmParams p{};
         p.M = R; p.N = Cp; p.K = D; p.bias = e->head.b; p.out = lg; p.ldo = Cp;
         ProfScope ps(e, PK_HEAD, 2.0 * p.M * C * p.K, s);
-        if (launch_gemm(e, e->cta_group, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, tmX, p, s, e->num_sms)) return 1;
+        if (launch_gemm(e, e->cta_group, e->head.bn, EPI_BIAS_F32, e->tmA_C, e->head.tm, tmX, tmX, p, s, e->num_sms)) return 1;
     }
     if (d_logits && lg != d_logits)
         CUDA_TRY(cudaMemcpy2DAsync(d_logits, (size_t)C * 4, lg, (size_t)Cp * 4, (size_t)C * 4, (size_t)R, cudaMemcpyDeviceToDevice, s));
@@ -990,6 +1015,14 @@ static int create_impl(const vitb200_hparams *hp, const vitb200_tensor *t, int n
         if (cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) != cudaSuccess)
             return bail(fail("cudaEventCreate failed"));
+    {
+        // Fused LayerNorm (residual epilogue + dedicated LayerNorm warps, gemm_tcgen05.cuh): bit-identical to the stand-alone kernel but
+        // SLOWER on B200 at batch 256 (proj + LN 2.78 ms vs 1.15 + 0.60 ms per forward), so it is opt-in
+        // (VITB200_FUSED_LN=1).  It needs the whole row in N % 128 == 0 float4-per-lane form and w, b in shared memory.
+        const bool want = getenv("VITB200_FUSED_LN") && atoi(getenv("VITB200_FUSED_LN")) == 1;
+        e->fused_ln = want && D % 128 == 0 && D <= 1024;
+        if (e->fused_ln && dev_alloc(e, &e->d_ln_count, (T + 255) / 256 * 8 + 8)) return bail(1);
+    }
     if (pa_alias) e->PA = e->H16;
     else
     {
@@ -997,8 +1030,7 @@ static int create_impl(const vitb200_hparams *hp, const vitb200_tensor *t, int n
         if (cudaMemset(e->PA, 0, pa_elems * sizeof(__half)) != cudaSuccess) return bail(fail("cudaMemset failed"));
     }
     if (make_tmap(&e->tmA_D, e->A16, T, D, D, GEMM_BM) || make_tmap(&e->tmA_H, e->H16, T, 4 * (uint64_t)D, 4 * (uint64_t)D, GEMM_BM) ||
-        make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, R, D, D, GEMM_BM) ||
-        make_tmap_f32_box32(&e->tmX, e->X, T, D, D))
+        make_tmap(&e->tmA_P, e->PA, B * e->NP, e->KPp, e->KPp, GEMM_BM) || make_tmap(&e->tmA_C, e->CLS16, R, D, D, GEMM_BM))
         return bail(1);
     {
         const char *force = getenv("VITB200_ATTENTION"); // bring-up knob: "mma" forces the warp-MMA kernel
@@ -1408,9 +1440,12 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
         }
         const int bn = pick_bn(N);
         const int cg = (getenv("VITB200_CTA_GROUP") && atoi(getenv("VITB200_CTA_GROUP")) == 1) ? 1 : 2;
-        CUtensorMap tA, tB, tX;
+        CUtensorMap tA, tB, tX, tO2;
         if (make_tmap(&tA, dA, M, K, K, GEMM_BM) || make_tmap(&tB, dW, N, K, K, bn / cg)) break;
         memset(&tX, 0, sizeof(tX));
+        memset(&tO2, 0, sizeof(tO2));
+        if (f16out && make_tmap(&tX, dO, M, N, N, 32)) break;            // the f16 epilogues store through TMA
+        if (dO2 && make_tmap(&tO2, dO2, M, N, N, 32)) break;
         if (epilogue == EPI_BIAS_RESID_F32)
         {
             // the residual epilogue works in place on the f32 stream, like the engine uses it (X += ...)
@@ -1419,7 +1454,7 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
         }
         GemmParams p{};
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dO; p.out2 = dO2; p.ldo = N; p.resid = (const float *)dO;
-        if (launch_gemm(nullptr, cg, bn, epilogue, tA, tB, tX, p, 0, prop.multiProcessorCount)) break;
+        if (launch_gemm(nullptr, cg, bn, epilogue, tA, tB, tX, tO2, p, 0, prop.multiProcessorCount)) break;
         cudaError_t err = cudaDeviceSynchronize();
         if (err != cudaSuccess) { fail("GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
         if (f16out)

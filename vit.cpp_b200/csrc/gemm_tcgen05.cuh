@@ -48,6 +48,15 @@ struct GemmParams
     int np, ntok;       // EPI_PATCH_F32: patches / tokens per image
     const float *img;   // EPI_PATCH_GATHER_F32: images [B][S][S][3] f32 (image_f32 layout, vit.h:98-103)
     int S, G;           // EPI_PATCH_GATHER_F32: image side, patches per side
+    // EPI_BIAS_RESID_F32 with a fused LayerNorm (N == hidden size, N % 128 == 0, N <= 1024): the LayerNorm that follows the residual add
+    // (vit.cpp:881-885 after proj, vit.cpp:808-812 of the next block after fc2) is applied to every 32-row group as soon as ALL of
+    // its column tiles have been stored -- by whichever epilogue warp stores the last one (ln_count: one counter per 32-row group,
+    // zero on entry and left zero) -- while the rows are still in L2; ln_out receives the f16 rows [M][N].  NULL = no fusion.
+    __half *ln_out;
+    const float *ln_w, *ln_b;
+    int *ln_count;
+    float ln_eps;
+    int ln_dbg;         // dev knob (VITB200_LN_DBG): bit 0 = epilogue side without the GPU-scope fences, bit 1 = LayerNorm side without
 };
 
 constexpr int GEMM_BM = 128;
@@ -75,13 +84,19 @@ struct GemmCfg
     static constexpr int kEpiWarps = kResid ? 4 : 8;
     static constexpr int kGatherWarps = kGather ? 4 : 0; // patch-embedding A producers (thread = one patch row of the tile)
     static constexpr int kFirstEpiWarp = 2 + kGatherWarps;
-    static constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+    static constexpr int kLnWarps = kResid ? 8 : 0;      // residual epilogue: dedicated LayerNorm warps behind a shared-memory work queue
+    static constexpr int kLnItemRows = 16;               // rows per work item (half a 32-row group)
+    static constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps + kLnWarps);
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_ROWS = BN / CG;               // W rows staged by this CTA
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = kResid ? 4 * kResidRing * 4096 : kEpiWarps * 4096; // per epilogue warp: ring or transpose buffer
     static constexpr int BAR_BYTES = 512;
-    static constexpr int BIAS_BYTES = kF16Out ? kEpiWarps * 512 : 0; // per-warp bias strips (f16 epilogues)
+    // per-warp bias strips: 128 values (f16 epilogues), BN values (residual epilogue); + LayerNorm weight and bias (2 x 1024 floats)
+    // for the residual epilogue's fused LayerNorm
+    static constexpr int kLnMaxD = 1024;
+    static constexpr int kLnQueue = 256;                 // work-queue slots (8-row items), with flow control
+    static constexpr int BIAS_BYTES = kF16Out ? kEpiWarps * 512 : (kResid ? 4 * BN * 4 + 2 * kLnMaxD * 4 + kLnQueue * 4 + 64 : 0);
     static constexpr int kSmemLimit = 232448; // 227 KB per CTA
     static constexpr int kStagesFit = (kSmemLimit - 1024 - STAGE_BYTES - BAR_BYTES - BIAS_BYTES) / (A_BYTES + B_BYTES);
     static constexpr int kStagesFit8 = kStagesFit > 8 ? 8 : kStagesFit;
@@ -119,11 +134,59 @@ __device__ __forceinline__ void gelu_tanh_f32x2(float x0, float x1, float &y0, f
     ptx::unpack_f32x2(ptx::mul_f32x2(x, ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1))), y0, y1);
 }
 
+// One warp normalises one row of X (f32, already complete in L2) into the f16 A operand of the next GEMM: the arithmetic of
+// layernorm_f16_kernel (kernels.cuh) -- f32 two-pass mean / biased variance, then ((x - mean) * scale) * w + b as three separately
+// rounded operations (the reference's NORM, MUL, ADD nodes, ggml.c:8959-9008, vit.cpp:808-812), RNE to f16 -- with w and b read from
+// shared memory and the row read past L1 (ld.global.cg: other SMs wrote it).  nv = D / 128 float4 per lane (<= 8).
+__device__ __forceinline__ void ln_row_load(const float *xrow, int nv, int lane, float4 (&v)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < nv) v[j] = __ldcg(reinterpret_cast<const float4 *>(xrow) + lane + 32 * j);
+}
+__device__ __forceinline__ void ln_row_finish(float4 (&v)[8], int nv, int D, int lane, const float4 *w4, const float4 *b4, float eps, __half *yrow)
+{
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < nv) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < nv)
+        {
+            v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+            sq += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float scale = 1.0f / sqrtf(sq / (float)D + eps);
+    uint2 *yr = reinterpret_cast<uint2 *>(yrow);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < nv)
+        {
+            const int i = lane + 32 * j;
+            const float4 ww = w4[i], bb = b4[i];
+            const __half2 h0 = __floats2half2_rn(__fadd_rn(__fmul_rn(__fmul_rn(v[j].x, scale), ww.x), bb.x), __fadd_rn(__fmul_rn(__fmul_rn(v[j].y, scale), ww.y), bb.y));
+            const __half2 h1 = __floats2half2_rn(__fadd_rn(__fmul_rn(__fmul_rn(v[j].z, scale), ww.z), bb.z), __fadd_rn(__fmul_rn(__fmul_rn(v[j].w, scale), ww.w), bb.w));
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t *>(&h0);
+            u.y = *reinterpret_cast<const uint32_t *>(&h1);
+            yr[i] = u;
+        }
+}
+
 template <int BN, int EPI, int DEEPK, int CG>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI == EPI_BIAS_RESID_F32, CG, EPI == EPI_PATCH_GATHER_F32, DEEPK != 0,
                                            EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_F16_HILO>::kThreads), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmX, const GemmParams p)
+                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO2, const GemmParams p)
+// tmX: EPI_BIAS_RESID_F32 -- the f32 residual/output stream (32 x 32 boxes); f16 epilogues -- the f16 OUTPUT tensor (64-column x 32-row
+// boxes, SWIZZLE_128B), tmO2 -- the lo tensor of EPI_BIAS_F16_HILO.  Unused maps are ignored.
 {
     constexpr bool kResid = (EPI == EPI_BIAS_RESID_F32);
     constexpr bool kGather = (EPI == EPI_PATCH_GATHER_F32);
@@ -167,7 +230,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
-        if constexpr (kResid) ptx::prefetch_tensormap(&tmX);
+        if constexpr (kResid || kOutF16) ptx::prefetch_tensormap(&tmX);
+        if constexpr (kHiLo) ptx::prefetch_tensormap(&tmO2);
     }
     if (warp_idx == 1 && lane == 0)
     {
@@ -183,8 +247,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_init(tempty_bar(a), CG * Cfg::kEpiWarps); // one arrival per epilogue warp of the group (leader's barrier)
         }
         if constexpr (kResid)
+        {
             for (int w = 0; w < 4; ++w)
                 for (int r = 0; r < Cfg::kResidRing; ++r) ptx::mbar_init(rfull_bar(w, r), 1);
+            // LayerNorm work-queue counters (reserved, published, claimed, consumed)
+            int *qctl = reinterpret_cast<int *>(smem + kStages * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STAGE_BYTES + Cfg::BAR_BYTES + 4 * BN * 4 +
+                                                2 * Cfg::kLnMaxD * 4 + Cfg::kLnQueue * 4);
+            qctl[0] = qctl[1] = qctl[2] = qctl[3] = 0;
+        }
         ptx::fence_barrier_init();
     }
     if (warp_idx == Cfg::kFirstEpiWarp)
@@ -364,6 +434,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     }
+    else if (kResid && warp_idx >= Cfg::kFirstEpiWarp + Cfg::kEpiWarps)
+    {
+        // ===================== LayerNorm warps (residual epilogue with a fused LayerNorm) =====================
+        // Work items are 16-row halves of 32-row groups whose every column tile has been stored (published by the epilogue warps
+        // below through a shared-memory queue); any LayerNorm warp takes the next item, reads the rows from L2 (they were written
+        // moments ago), normalises them (ln_row_finish) and writes the f16 A operand of the next GEMM.  A -1 item ends a warp.
+        if constexpr (kResid)
+        {
+            if (p.ln_out != nullptr)
+            {
+                uint8_t *extra = smem + kStages * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+                float *lnw = reinterpret_cast<float *>(extra + 4 * BN * 4);
+                const float4 *lnw4 = reinterpret_cast<const float4 *>(lnw);
+                const float4 *lnb4 = lnw4 + Cfg::kLnMaxD / 4;
+                volatile int *qbuf = reinterpret_cast<volatile int *>(extra + 4 * BN * 4 + 2 * Cfg::kLnMaxD * 4);
+                int *qctl = const_cast<int *>(qbuf) + Cfg::kLnQueue; // [0] reserved, [1] published (tail), [2] claimed (head), [3] consumed
+                const int lw = warp_idx - (Cfg::kFirstEpiWarp + Cfg::kEpiWarps);
+                for (int i = lw * 32 + lane; i < p.N; i += 32 * Cfg::kLnWarps) { lnw[i] = __ldg(p.ln_w + i); lnw[Cfg::kLnMaxD + i] = __ldg(p.ln_b + i); }
+                ptx::named_bar_sync(1, 32 * Cfg::kLnWarps); // the LayerNorm warps only
+                const int ln_nv = p.N >> 7;
+                const float *X = reinterpret_cast<const float *>(p.out);
+                for (;;)
+                {
+                    int row0 = 0;
+                    if (lane == 0)
+                    {
+                        const int idx = atomicAdd(&qctl[2], 1);
+                        while (*reinterpret_cast<volatile int *>(&qctl[1]) <= idx) __nanosleep(100);
+                        row0 = qbuf[idx % Cfg::kLnQueue];
+                        __threadfence_block();
+                        atomicAdd(&qctl[3], 1);
+                    }
+                    row0 = __shfl_sync(0xffffffffu, row0, 0);
+                    if (row0 < 0) break;
+                    // Three rows in flight per warp: while the GEMM saturates HBM a load takes several microseconds to come back, and
+                    // the eight warps together must keep ~10 rows (30 KB) in flight per SM to follow the rate at which rows complete.
+                    const int rows = (p.ln_dbg & 4) ? 0 : min(Cfg::kLnItemRows, p.M - row0);
+                    float4 va[8], vb[8], vc[8];
+                    if (rows > 0) ln_row_load(X + (size_t)row0 * p.ldo, ln_nv, lane, va);
+                    if (rows > 1) ln_row_load(X + (size_t)(row0 + 1) * p.ldo, ln_nv, lane, vb);
+                    if (rows > 2) ln_row_load(X + (size_t)(row0 + 2) * p.ldo, ln_nv, lane, vc);
+                    for (int r = 0; r < rows; r += 3)
+                    {
+                        ln_row_finish(va, ln_nv, p.N, lane, lnw4, lnb4, p.ln_eps, p.ln_out + (size_t)(row0 + r) * p.N);
+                        if (r + 3 < rows) ln_row_load(X + (size_t)(row0 + r + 3) * p.ldo, ln_nv, lane, va);
+                        if (r + 1 < rows) ln_row_finish(vb, ln_nv, p.N, lane, lnw4, lnb4, p.ln_eps, p.ln_out + (size_t)(row0 + r + 1) * p.N);
+                        if (r + 4 < rows) ln_row_load(X + (size_t)(row0 + r + 4) * p.ldo, ln_nv, lane, vb);
+                        if (r + 2 < rows) ln_row_finish(vc, ln_nv, p.N, lane, lnw4, lnb4, p.ln_eps, p.ln_out + (size_t)(row0 + r + 2) * p.N);
+                        if (r + 5 < rows) ln_row_load(X + (size_t)(row0 + r + 5) * p.ldo, ln_nv, lane, vc);
+                    }
+                }
+            }
+        }
+    }
     else
     {
         // ===================== epilogue warps (2..5) =====================
@@ -396,12 +520,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             };
             if (lane == 0)
                 for (int i = 0; i < R - 1; ++i) issue_next();
+            // shared-memory extras of this epilogue: per-warp bias strip (BN floats: with the 227 KB carve-out there is no L1 to speak
+            // of, a __ldg per chunk was an L2 round trip), then the fused LayerNorm's weight and bias
+            uint8_t *extra = smem + kStages * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+            float4 *bias_r4 = reinterpret_cast<float4 *>(extra) + ew * (BN / 4);
+            const bool fuse_ln = p.ln_out != nullptr;
+            volatile int *qbuf = reinterpret_cast<volatile int *>(extra + 4 * BN * 4 + 2 * Cfg::kLnMaxD * 4);
+            int *qctl = const_cast<int *>(qbuf) + Cfg::kLnQueue; // [0] reserved, [1] published (tail), [2] claimed (head), [3] consumed
+            auto load_bias_r = [&](int tile, int half) { // lane's float4 #half of the tile's bias (columns 4 (lane + 32 half) ..)
+                const int col = (tile % n_tiles) * BN + (lane + 32 * half) * 4;
+                return (tile < num_tiles && lane + 32 * half < BN / 4 && col < p.N) ? __ldg(reinterpret_cast<const float4 *>(p.bias + col))
+                                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            float4 bnext0 = load_bias_r(group_id, 0), bnext1 = load_bias_r(group_id, 1);
+            // lane 0: publish `k` items (first, first + 8, ...) or one sentinel to the LayerNorm warps: reserve, write, publish in order
+            auto q_push = [&](int first, int k) {
+                const int base = atomicAdd(&qctl[0], k);
+                while (base + k - *reinterpret_cast<volatile int *>(&qctl[3]) > Cfg::kLnQueue) __nanosleep(100); // flow control
+                for (int i = 0; i < k; ++i) qbuf[(base + i) % Cfg::kLnQueue] = first < 0 ? -1 : first + Cfg::kLnItemRows * i;
+                while (*reinterpret_cast<volatile int *>(&qctl[1]) != base) __nanosleep(20);
+                __threadfence_block();
+                *reinterpret_cast<volatile int *>(&qctl[1]) = base + k;
+            };
+            // "this warp's stores of row group `row0` have all completed": bump the group's counter; the warp that brings it to
+            // n_tiles (every column tile of those 32 rows is in L2 / HBM) hands the rows to the LayerNorm warps and resets the
+            // counter.  `pending` = bulk groups committed AFTER that tile's last store (they may still be in flight).
+            auto ln_signal = [&](int row0, int pending) {
+                if (lane == 0 && !(p.ln_dbg & 8))
+                {
+                    if (pending >= 4) ptx::tma_store_wait_group<4>(); else ptx::tma_store_wait_group<0>();
+                    if (!(p.ln_dbg & 1)) __threadfence();
+                    if (atomicAdd(p.ln_count + (row0 >> 5), 1) == n_tiles - 1)
+                    {
+                        p.ln_count[row0 >> 5] = 0;
+                        if (row0 < p.M) q_push(row0, min(32 / Cfg::kLnItemRows, (p.M - row0 + Cfg::kLnItemRows - 1) / Cfg::kLnItemRows));
+                    }
+                }
+                __syncwarp();
+            };
             int cons = 0;
+            int prev_row0 = -1; // row group of the previous tile, not yet signalled
             for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it)
             {
                 const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
+                bias_r4[lane] = bnext0;
+                if (BN > 128) bias_r4[lane + 32] = bnext1;
+                __syncwarp();
+                bnext0 = load_bias_r(tile + num_groups, 0);
+                bnext1 = load_bias_r(tile + num_groups, 1);
                 ptx::mbar_wait(tfull_bar(as), aphase);
                 ptx::tcgen05_fence_after();
                 const int m0 = m_blk * TILE_M + (int)cta_rank * GEMM_BM + q * 32;
@@ -426,9 +594,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                     {
-                        const int col = n0 + c * 32 + j * 4;
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (col < p.N) b = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                        const float4 b = bias_r4[c * 8 + j]; // zeros for columns >= N
                         float4 r = sl[lane * 8 + (j ^ sw)];
                         r.x = __fadd_rn(__fadd_rn(__uint_as_float(v[4 * j + 0]), b.x), r.x); // (mul_mat + b) + inpL, vit.cpp:869,873
                         r.y = __fadd_rn(__fadd_rn(__uint_as_float(v[4 * j + 1]), b.y), r.y);
@@ -447,8 +613,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         issue_next();
                     }
                     __syncwarp();
+                    // the previous tile's stores have had four chunk times to complete: signal its row group now (no stall)
+                    if (fuse_ln && prev_row0 >= 0 && (c == 3 || (c == nch - 1 && nch < 4)))
+                    {
+                        ln_signal(prev_row0, c == 3 ? 4 : 0);
+                        prev_row0 = -1;
+                    }
                 }
+                if (fuse_ln) prev_row0 = m0;
             }
+            if (fuse_ln && prev_row0 >= 0) ln_signal(prev_row0, 0);
+            if (fuse_ln && lane == 0) q_push(-1, Cfg::kLnWarps / 4); // sentinels: as many in total as there are LayerNorm warps
             if (lane == 0) ptx::tma_store_wait_read<0>();
             __syncwarp();
         }
@@ -516,13 +691,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
                 if constexpr (kOutF16)
                 {
-                    // math in the row-per-thread domain (bias is warp-uniform -> broadcast loads), pack to f16.  The hi-lo epilogue
-                    // runs the staging round trip twice over the same accumulator registers: part 0 emits hi = f16(x), part 1
-                    // recomputes x and hi and emits lo = f16(x - hi) (exact difference, |lo| <= 2^-11 |x|) to the second tensor.
-                    uint4 *stg4 = reinterpret_cast<uint4 *>(stg);
+                    // math in the row-per-thread domain (bias is warp-uniform -> broadcast loads from the strip), pack to f16 into this
+                    // warp's 32-row x 128-B staging box -- 16-B chunk j of row r at j ^ (r & 7), which is exactly TMA SWIZZLE_128B and
+                    // bank-conflict free -- then ONE TMA store per box: rows >= M and columns >= N are clipped by the tensor map.  (The
+                    // first version read the box back with LDS and issued 8 STG.128 per lane group: a third of the epilogue's
+                    // instructions and half of its LSU shared-memory wavefronts; ncu had the split-precision qkv epilogue at 72 %
+                    // tensor-pipe activity against 90 % for the plain one.)  The hi-lo epilogue runs the round trip twice over the same
+                    // accumulator registers: part 0 emits hi = f16(x), part 1 recomputes x and hi and emits lo = f16(x - hi) (exact
+                    // difference, |lo| <= 2^-11 |x|) to the second tensor.
+                    const uint32_t stg_u32 = ptx::smem_u32(stg);
 #pragma unroll
                     for (int part = 0; part < (kHiLo ? 2 : 1); ++part)
                     {
+                    if (lane == 0) ptx::tma_store_wait_read<0>(); // the previous box has left the staging buffer
+                    __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) // 8 chunks of 8 columns (16 B of f16)
                     {
@@ -556,22 +738,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                             packed[e] = *reinterpret_cast<uint32_t *>(&h);
                         }
-                        stg4[lane * 8 + (j ^ sw)] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        ptx::st_shared_v4(stg_u32 + (uint32_t)lane * 128u + (uint32_t)((j ^ sw) << 4), packed[0], packed[1], packed[2], packed[3]);
                     }
+                    ptx::fence_proxy_async_smem(); // generic-proxy writes -> visible to the TMA store (async proxy)
                     __syncwarp();
-                    __half *dst = reinterpret_cast<__half *>(part == 0 ? p.out : p.out2);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    if (lane == 0)
                     {
-                        const int row = i * 4 + (lane >> 3);
-                        const int ch = lane & 7;
-                        const uint4 val = stg4[row * 8 + (ch ^ (row & 7))];
-                        const int grow = m0 + row;
-                        const int gcol = n0 + c + ch * 8;
-                        if (grow < p.M && gcol < p.N)
-                            *reinterpret_cast<uint4 *>(dst + (size_t)grow * p.ldo + gcol) = val;
+                        ptx::tma_store_2d(part == 0 ? &tmX : &tmO2, stg_u32, n0 + c, m0);
+                        ptx::tma_store_commit();
                     }
-                    __syncwarp();
                     }
                 }
                 else
@@ -614,6 +789,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
                 }
             }
+        }
+        if constexpr (kOutF16)
+        {
+            if (lane == 0) ptx::tma_store_wait_all(); // shared memory must outlive the last box's read
+            __syncwarp();
         }
         } // !kResid
     }

@@ -193,6 +193,13 @@ __device__ __forceinline__ void tma_store_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// wait until at most N of this thread's most recent bulk groups are still pending (FULL completion: the global writes are done)
+template <int N>
+__device__ __forceinline__ void tma_store_wait_group()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tcgen05_alloc(uint32_t smem_dst, uint32_t ncols)
 {
