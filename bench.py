@@ -461,6 +461,37 @@ def main():
     e2e_value = world * B * args.steps / float(t.item())
     top1_check = int(h_idx[0][0, 0])
 
+    # ---- end to end from u8 images (what load_image_from_file hands to vit_image_preprocess, vit.h:91-96): 256 x 256 RGB u8 per image,
+    # packed + copied (4x fewer PCIe bytes than the f32 batch), resized / normalised on the GPU straight into the f16 patch matrix
+    rng = np.random.default_rng(77 + rank)
+    u8_batches = [[rng.integers(0, 256, size=(256, 256, 3), dtype=np.uint8) for _ in range(B)] for _ in range(2)]
+    u8_args = []
+    for imgs_u8 in u8_batches:
+        ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in imgs_u8])
+        nx = (C.c_int * B)(*[a.shape[1] for a in imgs_u8])
+        ny = (C.c_int * B)(*[a.shape[0] for a in imgs_u8])
+        u8_args.append((ptrs, nx, ny))
+
+    def step_u8(i):
+        j = i & 1
+        ptrs, nx, ny = u8_args[j]
+        rc = L.vitb200_forward_u8_async(model.handle, ptrs, nx, ny, B, 0, h_probs[j].data_ptr(), None, h_idx[j].data_ptr(), h_val[j].data_ptr(), 5)
+        if rc != 0:
+            raise RuntimeError(L.vitb200_last_error().decode())
+    for i in range(2):
+        step_u8(i)
+    L.vitb200_sync(model.handle)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_u8(i)
+    L.vitb200_sync(model.handle)
+    u8_s = time.perf_counter() - t0
+    t = torch.tensor([u8_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * B * args.steps / float(t.item())
+
     # optional tail of the north-star design: gather the top-k pairs on rank 0 over NCCL (not on the timed path)
     if world > 1:
         gathered = [torch.empty_like(d_idx) for _ in range(world)] if rank == 0 else None
@@ -478,6 +509,10 @@ def main():
                        "attention_operands": "split precision (hi + lo f16 pairs for q, k, v: the reference's f32-operand attention)" if os.environ.get("VITB200_ATTN_HILO", "1") != "0" else "f16 only (VITB200_ATTN_HILO=0)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
                     "d2h_bytes_per_step": B * (model.num_classes * 4 + 5 * 4 + 5 * 4)},
+            "e2e_u8": {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": B * 256 * 256 * 3 + B * 16,
+                       "d2h_bytes_per_step": B * (model.num_classes * 4 + 5 * 4 + 5 * 4),
+                       "what": "vitb200_forward_u8_async: 256x256 RGB u8 images from host memory -> pinned staging -> one H2D -> bicubic resize + normalise on the "
+                               "GPU (reference vit_image_preprocess semantics) -> forward -> probabilities + top-5 back to pinned host memory"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "sustained": {"value": sustained_value, "unit": "images/s", "steps": n_sus, "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus,

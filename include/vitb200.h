@@ -114,6 +114,14 @@ int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const
 int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
                        float *images_f32_out, float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k);
 
+/* Pipelined form (vitb200_forward_u8 == this + vitb200_sync, plus the optional f32 read-back): the images are packed into a pinned
+ * staging buffer inside the call (so `images` may be reused as soon as it returns), ONE host-to-device copy per batch overlaps the
+ * previous call's kernels, the pre-processed pixels go straight into the f16 patch matrix of the patch-embedding GEMM, and nothing
+ * synchronises or allocates in steady state.  Output buffers must stay valid until vitb200_sync().  Shares its two pipeline slots
+ * with vitb200_forward_async. */
+int vitb200_forward_u8_async(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
+                             float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k);
+
 /* Same with DEVICE buffers on the engine's device, enqueued on `stream` (a cudaStream_t; NULL = the engine's own
  * stream) without synchronising: the caller owns ordering.  This is the resident-data path bench.py times. */
 int vitb200_forward_device(vitb200_engine *e, const float *d_images, int batch, float *d_probs, float *d_logits,

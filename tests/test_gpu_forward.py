@@ -304,7 +304,7 @@ def test_fused_layernorm_path_is_bit_identical(monkeypatch):
         m.close()
         assert np.array_equal(got[3], want[3]) and np.array_equal(got[1], want[1])
         L = gf.CONFIGS[cfg][1]
-        assert launches == 3 + 5 * L + 1 + 3   # no LayerNorm launches except the first block's and the pooled final one
+        assert launches == 3 + 1 + 5 * L + 3   # patchify + cls rows + patch GEMM, first LayerNorm, 5 kernels per block, pooled LN + head + soft-max: no other LayerNorm launches except the first block's and the pooled final one
 
 
 def test_error_paths():
@@ -532,6 +532,55 @@ def test_batch_size_sweep_is_bit_identical_and_stable():
             assert np.array_equal(l[B - 1], want), (B, rep)
             assert np.isfinite(l).all() and abs(float(p.sum()) - B) < 1e-2 * B
     m.close()
+
+
+_BENCH_B200 = os.path.join(os.path.dirname(ref.VIT_REF_BIN), "benchmark_b200")
+
+
+@pytest.mark.skipif(not (os.path.exists(_BENCH_B200) and ref.available()), reason="accuracy harness binary (oracle/_ref) not shipped")
+def test_batched_accuracy_harness_on_a_synthetic_image_folder(tmp_path):
+    """The reference's accuracy harness (tests/benchmark.cpp: <dataset>/<class>/<image> folders, ../classnames.json, one
+    "file,true,predicted" line per image, "Top-1 Accuracy") running batched on the engine (integration/benchmark_b200.cpp: reference
+    image decoder, GPU preprocess + forward through vitb200_forward_u8_async, batch 4 here so the two pipeline slots and a ragged
+    last batch are exercised).  Expected predictions come from the reference pipeline itself (its preprocess + its vit_predict)."""
+    import json
+    import subprocess
+    rng = np.random.default_rng(21)
+    root = tmp_path / "data"
+    names = [f"class_{i}" for i in range(1000)]
+    (tmp_path / "classnames.json").write_text(json.dumps(names))
+    model = model_path("tiny", "f16")
+    rm = ref.RefModel(model)
+    expect = {}
+    dirs = ["class_7", "class_421", "class_900"]
+    n_imgs = 0
+    for d in dirs:
+        (root / d).mkdir(parents=True)
+        for j in range(3 if d != "class_900" else 5):
+            h, w = int(rng.integers(120, 300)), int(rng.integers(120, 300))
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = np.stack([(xx * 3 + j * 40) % 256, (yy * 2 + 90) % 256, rng.integers(0, 256, size=(h, w))], -1).astype(np.uint8)
+            with open(root / d / f"img{j}.ppm", "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (w, h) + img.tobytes())
+            p_ref, l_ref = rm.predict(rm.preprocess(img), n_threads=8)
+            order = np.argsort(-l_ref)
+            expect[(d, f"img{j}.ppm")] = (names[int(order[0])], float(l_ref[order[0]] - l_ref[order[1]]), float(np.abs(l_ref).max()))
+            n_imgs += 1
+        (root / d / "notes.txt").write_text("not an image")
+    rm.close()
+    out = tmp_path / "pred.txt"
+    r = subprocess.run([_BENCH_B200, model, str(root), "4", str(out), "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l.split(",") for l in out.read_text().splitlines()]
+    assert len(lines) == 3 + 3 + 4                      # num_images_per_class = 4 caps the 5-image class
+    correct = 0
+    for fname, truth, pred in lines:
+        want, gap, scale = expect[(truth, fname)]
+        if gap > 2.5e-3 * scale:                        # a top-1 decided by less than the parity noise may legitimately flip
+            assert pred == want, (fname, truth, pred, want)
+        correct += truth == pred
+    acc = [l for l in r.stdout.splitlines() if l.startswith("Top-1 Accuracy:")]
+    assert acc and abs(float(acc[0].split(":")[1].strip().rstrip("%")) - 100.0 * correct / len(lines)) < 1e-3
 
 
 _VITSTR_REF = os.path.join(os.path.dirname(ref.VIT_REF_BIN), "vitstr_ref")

@@ -1,3 +1,4 @@
-for m in 0 4 8; do echo "LN_DBG=$m"; VITB200_LN_DBG=$m timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-configs --sustained-seconds 0.2 2>/dev/null | python -c "
+python -m pytest tests/test_gpu_forward.py -x -q -k "preprocess or u8 or golden or fused or cli" 2>&1 | tail -3
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-configs 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.readline()); print(round(d['value']), {k:round(v['ms_per_step'],3) for k,v in d['kernels'].items()}, d['parity']['median'])"; done
+d=json.loads(sys.stdin.readline()); print(round(d['value']), 'e2e', round(d['e2e']['value']), 'e2e_u8', round(d['e2e_u8']['value']), 'sust', round(d['sustained']['value']), d['gpu_launches'], {k:round(v['ms_per_step'],3) for k,v in d['kernels'].items()}, d['parity']['median'], d['clocks'])"

@@ -10,6 +10,7 @@
 #include "gguf_file.hpp"
 #include "preprocess.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -179,10 +180,10 @@ struct vitb200_engine
     int32_t *d_topk_idx_slot[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     unsigned long long submits = 0;
-    // GPU preprocessing (vitb200_forward_u8): u8 staging buffer + per-image descriptors, grown on demand
-    uint8_t *d_u8 = nullptr;
-    size_t d_u8_cap = 0;
-    PreImage *d_pre = nullptr;
+    // GPU preprocessing (vitb200_forward_u8*): per pipeline slot a PINNED host staging buffer (the caller's images are packed into it,
+    // followed by the per-image descriptors) and its device twin; grown only when a batch needs more than any batch before it
+    uint8_t *h_u8[2] = {nullptr, nullptr}, *d_u8[2] = {nullptr, nullptr};
+    size_t u8_cap[2] = {0, 0};
     // CUDA-graph cache for the kernel schedule of one forward, keyed by its arguments (launch-bound inner loop: ~90 kernels)
     struct GraphEntry { const void *img; int batch; void *probs, *logits, *tidx, *tval; int k; int state; int launches; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;
@@ -516,7 +517,13 @@ int launch_patchify(vitb200_engine *e, const float *img, __half *A, int B, cudaS
     }
     switch (e->hp.patch_size)
     {
-    case 16: patchify_f16_kernel<16><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
+    case 16:
+    {
+        const int n_patches = B * e->G * e->G; // one warp per patch, grid-stride over a few waves
+        const int wblocks = std::min((n_patches + 7) / 8, e->num_sms * 16);
+        patchify16_warp_kernel<<<wblocks, 256, 0, s>>>(img, A, n_patches, e->hp.img_size, e->G, e->KPp);
+        break;
+    }
     case 14: patchify_f16_kernel<14><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
     case 8: patchify_f16_kernel<8><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
     case 32: patchify_f16_kernel<32><<<blocks, threads, 0, s>>>(img, A, B, e->hp.img_size, e->G, e->KPp); break;
@@ -688,6 +695,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
 {
     if (B < 1 || B > e->max_batch) return fail("batch %d out of range (1..%d)", B, e->max_batch);
     if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
+    if (!d_images && taps) return fail("debug taps need the f32 image path");
     const int D = e->hp.hidden_size, N = e->N, T = B * N, C = e->hp.num_classes;
     e->launches = 0;
     __half *PA = e->PA;
@@ -707,23 +715,28 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
     }
     const CUtensorMap &tmX = bm->second.X, &tmQKVh = bm->second.QKVh, &tmQKVl = bm->second.QKVl, &tmH = bm->second.H;
 
-    // patch embedding (vit.cpp:772-797).  P = 16 with CTA pairs: ONE kernel -- the GEMM's A producers gather the f32 pixels
-    // straight into the tcgen05 operand tiles (no im2col buffer) and the epilogue adds conv bias + pos_embed and writes token
-    // rows.  Other patch sizes: patchify_f16_kernel materialises the f16 patch matrix first.
-    const bool fused_patch = e->hp.patch_size == 16 && e->cta_group == 2 && e->C == 3;
-    if (!fused_patch && launch_patchify(e, d_images, PA, B, s)) return 1;
-    {
-        const int n = B * D, threads = 256;
-        cls_rows_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(e->X, e->cls, e->pos, B, N, D);
-        CUDA_TRY(cudaGetLastError());
-        e->launches++;
-    }
+    // patch embedding (vit.cpp:772-797): the f16 patch matrix PA (im2col of a stride == kernel conv is a pure permutation,
+    // ggml.c:11528-11608) is either already there (d_images == NULL: the u8 path's preprocess kernel wrote it) or written by
+    // patchify (one warp per patch, coalesced); the TMA-fed GEMM adds conv bias + pos_embed and writes token rows.
+    // VITB200_PATCH_GATHER=1 (P = 16, CTA pairs, 3 channels) selects the single-kernel variant whose A producers gather the f32
+    // pixels straight into the operand tiles: no patch matrix, but its dependent 128-bit loads are L2-latency bound on an SM with no
+    // L1 left (0.29 ms against 0.05 + 0.10 ms at batch 256, profiles/), so it is no longer the default.
+    const bool patches_ready = d_images == nullptr;
+    const bool fused_patch = !patches_ready && e->hp.patch_size == 16 && e->cta_group == 2 && e->C == 3 &&
+                             getenv("VITB200_PATCH_GATHER") && atoi(getenv("VITB200_PATCH_GATHER")) == 1;
     {
         GemmParams p{};
         p.M = B * e->NP; p.N = D; p.K = e->KPp; p.bias = e->patch.b; p.out = e->X; p.ldo = D;
         p.pos = e->pos; p.np = e->NP; p.ntok = N;
         p.img = d_images; p.S = e->hp.img_size; p.G = e->G;
         ProfScope ps(e, PK_PATCH, 2.0 * p.M * p.N * e->KP, s);
+        if (!patches_ready && !fused_patch && launch_patchify(e, d_images, PA, B, s)) return 1;
+        {
+            const int n = B * D, threads = 256;
+            cls_rows_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(e->X, e->cls, e->pos, B, N, D);
+            CUDA_TRY(cudaGetLastError());
+            e->launches++;
+        }
         if (launch_gemm(e, e->cta_group, e->patch.bn, fused_patch ? EPI_PATCH_GATHER_F32 : EPI_PATCH_F32, e->tmA_P, e->patch.tm, tmX, tmX, p, s, e->num_sms)) return 1;
     }
     if (taps && tap_f32(taps->embed, e->X, (size_t)T * D, s)) return 1;
@@ -1074,8 +1087,7 @@ void vitb200_destroy(vitb200_engine *e)
     cudaSetDevice(e->device);
     for (void *p : e->allocs) cudaFree(p);
     for (auto &g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    if (e->d_u8) cudaFree(e->d_u8);
-    if (e->d_pre) cudaFree(e->d_pre);
+    for (int i = 0; i < 2; ++i) { if (e->d_u8[i]) cudaFree(e->d_u8[i]); if (e->h_u8[i]) cudaFreeHost(e->h_u8[i]); }
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1350,59 +1362,96 @@ int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, flo
 }
 
 // vit_image_preprocess (reference vit.cpp:289-305) for a batch of u8 RGB images of arbitrary sizes, on the GPU, followed by the
-// forward pass: the "images" of vitb200_forward never exist on the host.  images_f32_out (optional, HOST) receives the
-// pre-processed image_f32 batch for inspection.
-int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
-                       float *images_f32_out, float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k)
+// forward pass: the "images" of vitb200_forward never exist on the host, and (unless images_f32_out asks for them) not in HBM
+// either -- the preprocess kernel writes the f16 patch matrix the patch-embedding GEMM reads.  Pipelined like
+// vitb200_forward_async: the caller's images are packed into this slot's pinned staging buffer, ONE host-to-device copy on the copy
+// stream overlaps the previous call's kernels, nothing synchronises on entry and nothing is allocated once the staging buffers
+// have grown to the largest batch seen.
+static int forward_u8_enqueue(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
+                              float *images_f32_out, float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k)
 {
     if (!e || !images || !nx || !ny) return fail("null argument");
     if (e->C != 3) return fail("vitb200_forward_u8 implements vit_image_preprocess (RGB, vit.cpp:289-305); this model takes %d-channel input", e->C);
     if (batch < 1 || batch > e->max_batch) return fail("batch %d out of range (1..%d)", batch, e->max_batch);
     if (k < 0 || k > e->max_k) return fail("k %d out of range (0..%d)", k, e->max_k);
-    CUDA_TRY(cudaSetDevice(e->device));
-    CUDA_TRY(vitb200_sync(e) == 0 ? cudaSuccess : cudaErrorUnknown); // the staging buffer is not double-buffered
-    std::vector<PreImage> pre((size_t)batch);
     size_t total = 0;
     for (int b = 0; b < batch; ++b)
     {
         if (!images[b] || nx[b] < 1 || ny[b] < 1) return fail("image %d: bad pointer or size", b);
-        pre[b].offset = total; pre[b].nx = nx[b]; pre[b].ny = ny[b];
         total += ((size_t)nx[b] * ny[b] * 3 + 255) / 256 * 256;
     }
-    if (total > e->d_u8_cap)
+    const size_t table_off = total;
+    total += (size_t)batch * sizeof(PreImage);
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int sl = (int)(e->submits & 1);
+    cudaStream_t s = e->stream, cs = e->copy_stream;
+    // this slot's previous call (two submissions ago) must have consumed its staging buffer before the host overwrites it
+    if (e->submits >= 2) CUDA_TRY(cudaEventSynchronize(e->ev_done[sl]));
+    if (total > e->u8_cap[sl])
     {
-        if (e->d_u8) cudaFree(e->d_u8);
-        e->d_u8 = nullptr; e->d_u8_cap = 0;
-        CUDA_TRY(cudaMalloc((void **)&e->d_u8, total));
-        e->d_u8_cap = total;
+        const size_t cap = total + total / 4;
+        if (e->h_u8[sl]) cudaFreeHost(e->h_u8[sl]);
+        if (e->d_u8[sl]) cudaFree(e->d_u8[sl]);
+        e->h_u8[sl] = nullptr; e->d_u8[sl] = nullptr; e->u8_cap[sl] = 0;
+        CUDA_TRY(cudaHostAlloc((void **)&e->h_u8[sl], cap, cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc((void **)&e->d_u8[sl], cap));
+        e->u8_cap[sl] = cap;
     }
-    if (!e->d_pre) CUDA_TRY(cudaMalloc((void **)&e->d_pre, (size_t)e->max_batch * sizeof(PreImage)));
-    cudaStream_t s = e->stream;
+    PreImage *table = reinterpret_cast<PreImage *>(e->h_u8[sl] + table_off);
+    size_t off = 0;
     for (int b = 0; b < batch; ++b)
-        CUDA_TRY(cudaMemcpyAsync(e->d_u8 + pre[b].offset, images[b], (size_t)nx[b] * ny[b] * 3, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(e->d_pre, pre.data(), (size_t)batch * sizeof(PreImage), cudaMemcpyHostToDevice, s));
+    {
+        const size_t n = (size_t)nx[b] * ny[b] * 3;
+        memcpy(e->h_u8[sl] + off, images[b], n);
+        table[b].offset = off; table[b].nx = nx[b]; table[b].ny = ny[b];
+        off += (n + 255) / 256 * 256;
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->d_u8[sl], e->h_u8[sl], total, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaEventRecord(e->ev_h2d[sl], cs));
+    CUDA_TRY(cudaStreamWaitEvent(s, e->ev_h2d[sl], 0));
     const int S = e->hp.img_size;
     dim3 grid((unsigned)((S * S + 255) / 256), (unsigned)batch);
-    preprocess_kernel<<<grid, 256, 0, s>>>(e->d_u8, e->d_pre, e->d_img, S, bilinear ? 1 : 0);
+    float *d_f32 = images_f32_out ? e->d_img_slot[sl] : nullptr;
+    preprocess_kernel<<<grid, 256, 0, s>>>(e->d_u8[sl], reinterpret_cast<const PreImage *>(e->d_u8[sl] + table_off), d_f32, S, bilinear ? 1 : 0,
+                                           e->PA, e->hp.patch_size, e->KPp);
     CUDA_TRY(cudaGetLastError());
     const size_t img_elems = (size_t)3 * S * S;
-    if (images_f32_out) CUDA_TRY(cudaMemcpyAsync(images_f32_out, e->d_img, (size_t)batch * img_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (images_f32_out) CUDA_TRY(cudaMemcpyAsync(images_f32_out, d_f32, (size_t)batch * img_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     const bool want_topk = k > 0 && (topk_idx || topk_prob);
     const int C = e->hp.num_classes;
     if (probs || logits || want_topk)
     {
-        if (run_forward_graphed(e, e->d_img, batch, (probs || want_topk) ? e->d_probs : nullptr, e->d_logits_slot[0], want_topk ? e->d_topk_idx : nullptr,
-                                want_topk ? e->d_topk_val : nullptr, want_topk ? k : 0, s))
+        float *dp = (probs || want_topk) ? e->d_probs_slot[sl] : nullptr;
+        if (run_forward_graphed(e, nullptr, batch, dp, e->d_logits_slot[sl], want_topk ? e->d_topk_idx_slot[sl] : nullptr,
+                                want_topk ? e->d_topk_val_slot[sl] : nullptr, want_topk ? k : 0, s))
             return 1;
-        e->launches += 1;
+        e->launches += 1; // the preprocess kernel
         const size_t rows = (size_t)batch * e->head_tokens;
-        if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs, rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits_slot[0], rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx, rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val, rows * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (probs) CUDA_TRY(cudaMemcpyAsync(probs, e->d_probs_slot[sl], rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, e->d_logits_slot[sl], rows * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (want_topk && topk_idx) CUDA_TRY(cudaMemcpyAsync(topk_idx, e->d_topk_idx_slot[sl], rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (want_topk && topk_prob) CUDA_TRY(cudaMemcpyAsync(topk_prob, e->d_topk_val_slot[sl], rows * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
-    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaEventRecord(e->ev_done[sl], s));
+    e->submits++;
     return 0;
+}
+
+int vitb200_forward_u8_async(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
+                             float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k)
+{
+    VB_NOEXCEPT_BEGIN
+    return forward_u8_enqueue(e, images, nx, ny, batch, bilinear, nullptr, probs, logits, topk_idx, topk_prob, k);
+    VB_NOEXCEPT_END((void)0)
+}
+
+int vitb200_forward_u8(vitb200_engine *e, const uint8_t *const *images, const int *nx, const int *ny, int batch, int bilinear,
+                       float *images_f32_out, float *probs, float *logits, int32_t *topk_idx, float *topk_prob, int k)
+{
+    VB_NOEXCEPT_BEGIN
+    if (forward_u8_enqueue(e, images, nx, ny, batch, bilinear, images_f32_out, probs, logits, topk_idx, topk_prob, k)) return 1;
+    return vitb200_sync(e);
+    VB_NOEXCEPT_END((void)0)
 }
 
 int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W, const float *bias,

@@ -751,8 +751,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 else
                 {
-                    // raw accumulators through the transpose buffer; bias / residual / pos math on the coalesced side
+                    // raw accumulators through the transpose buffer; bias / residual / pos math on the coalesced side.  The bias and
+                    // pos_embed operands do not depend on the accumulator: they are requested BEFORE the staging round trip (there is no
+                    // L1 to speak of next to 227 KB of shared memory, so each of these loads is an L2 round trip that used to sit,
+                    // serialised, between the LDS and the store of every 16 bytes).
                     float4 *stg4 = reinterpret_cast<float4 *>(stg);
+                    const int ch = lane & 7;
+                    const int gcol = n0 + c + ch * 4;
+                    const bool col_ok = gcol < p.N;
+                    const float4 b = col_ok ? __ldg(reinterpret_cast<const float4 *>(p.bias + gcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 pe[kPatch ? 8 : 1];
+                    size_t orow_[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                    {
+                        const int grow = m0 + i * 4 + (lane >> 3);
+                        orow_[i] = (size_t)grow;
+                        if constexpr (kPatch)
+                        {
+                            const int img = grow / p.np, pp = grow - img * p.np;
+                            orow_[i] = (size_t)img * p.ntok + 1 + pp;
+                            pe[i] = (grow < p.M && col_ok) ? __ldg(reinterpret_cast<const float4 *>(p.pos + (size_t)(1 + pp) * p.N + gcol))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         stg4[lane * 8 + (j ^ sw)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -762,15 +784,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int i = 0; i < 8; ++i)
                     {
                         const int row = i * 4 + (lane >> 3);
-                        const int ch = lane & 7;
                         float4 a = stg4[row * 8 + (ch ^ (row & 7))];
                         const int grow = m0 + row;
-                        const int gcol = n0 + c + ch * 4;
-                        if (grow < p.M && gcol < p.N)
+                        if (grow < p.M && col_ok)
                         {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + gcol));
                             a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
-                            size_t orow = (size_t)grow;
                             if constexpr (EPI == EPI_BIAS_RESID_F32)
                             {
                                 const float4 r = *reinterpret_cast<const float4 *>(p.resid + (size_t)grow * p.ldo + gcol);
@@ -778,12 +796,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                             if constexpr (kPatch)
                             {
-                                const int img = grow / p.np, pp = grow - img * p.np;
-                                orow = (size_t)img * p.ntok + 1 + pp;
-                                const float4 r = __ldg(reinterpret_cast<const float4 *>(p.pos + (size_t)(1 + pp) * p.N + gcol));
+                                const float4 r = pe[i];
                                 a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
                             }
-                            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + orow * p.ldo + gcol) = a;
+                            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + orow_[i] * p.ldo + gcol) = a;
                         }
                     }
                     __syncwarp();

@@ -54,6 +54,42 @@ __global__ void patchify_f16_kernel(const float *__restrict__ img, __half *__res
     }
 }
 
+// P = 16, 3 channels: one WARP per patch.  Lane (ky = lane / 2, half = lane % 2) reads the 8 pixels x 3 channels (96 contiguous bytes)
+// of its half kernel row and writes, per channel, the 8 f16 values at k = c*256 + ky*16 + half*8: the warp's stores are three fully
+// coalesced 512-byte runs of the patch's A row, its loads sixteen 192-byte row segments.  (The thread-per-kernel-row mapping above
+// scatters 32-byte stores over 32 different A rows per warp: 1.5 TB/s at batch 256.)
+__global__ void patchify16_warp_kernel(const float *__restrict__ img, __half *__restrict__ A, int n_patches, int S, int G, int ldk)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pidx < n_patches; pidx += warps)
+    {
+        const int b = pidx / (G * G), pp = pidx - b * G * G, py = pp / G, px = pp - py * G;
+        const int ky = lane >> 1, half = lane & 1;
+        const float4 *src = reinterpret_cast<const float4 *>(img + (((size_t)b * S + (size_t)(py * 16 + ky)) * S + (size_t)px * 16 + half * 8) * 3);
+        float v[24];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+        {
+            const float4 f = __ldg(src + i);
+            v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+        }
+        __half *dst = A + (size_t)pidx * ldk + ky * 16 + half * 8;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+        {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+            {
+                const __half2 h2 = __floats2half2_rn(v[(2 * e) * 3 + c], v[(2 * e + 1) * 3 + c]); // RNE, ggml.c:11599
+                w[e] = *reinterpret_cast<const uint32_t *>(&h2);
+            }
+            *reinterpret_cast<uint4 *>(dst + c * 256) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 // x[b*ntok + 0][:] = cls[:] + pos[0][:]
 __global__ void cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls, const float *__restrict__ pos, int B, int ntok, int D)
 {

@@ -37,8 +37,11 @@ __device__ __forceinline__ float pre_cubic(float p0, float p1, float p2, float p
     return r;
 }
 
+// out (image_f32 batch, may be NULL) and/or patches (may be NULL): the f16 patch matrix the patch-embedding GEMM reads through TMA,
+// row = (image, patch), k = c*P*P + ky*P + kx (ggml.c:11597-11599), row pitch ldk -- written directly so that the f32 image never
+// exists in HBM on the u8 path (the reference rounds the pixels to f16 for the conv anyway, ggml.c:11599).
 __global__ void preprocess_kernel(const uint8_t *__restrict__ staging, const PreImage *__restrict__ imgs, float *__restrict__ out,
-                                  int S, int bilinear)
+                                  int S, int bilinear, __half *__restrict__ patches, int P, int ldk)
 {
     const int b = blockIdx.y;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,7 +52,8 @@ __global__ void preprocess_kernel(const uint8_t *__restrict__ staging, const Pre
     const int nx = im.nx, ny = im.ny;
     const float m3[3] = {123.675f, 116.280f, 103.530f}; // vit.cpp:233-234
     const float s3[3] = {58.395f, 57.120f, 57.375f};
-    float *dst = out + ((size_t)b * S * S + idx) * 3;
+    float px3[3];
+    float *dst = px3;
     if (!bilinear)
     {
         const float tx = __fdiv_rn((float)nx, (float)S), ty = __fdiv_rn((float)ny, (float)S);
@@ -90,6 +94,18 @@ __global__ void preprocess_kernel(const uint8_t *__restrict__ staging, const Pre
             const float r = fminf(fmaxf(roundf(v), 0.0f), 255.0f);
             dst[k] = __fdiv_rn((float)(uint8_t)r - m3[k], s3[k]);
         }
+    }
+    if (out)
+    {
+        float *o = out + ((size_t)b * S * S + idx) * 3;
+        o[0] = px3[0]; o[1] = px3[1]; o[2] = px3[2];
+    }
+    if (patches)
+    {
+        const int G = S / P, py = i / P, ky = i - py * P, pxi = j / P, kx = j - pxi * P;
+        __half *row = patches + ((size_t)b * G * G + (size_t)py * G + pxi) * ldk + ky * P + kx;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) row[k * P * P] = __float2half_rn(px3[k]);
     }
 }
 

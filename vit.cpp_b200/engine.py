@@ -75,6 +75,7 @@ def lib():
         L.vitb200_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.vitb200_forward_sharded.argtypes = [vp, i32, f32p, i32, f32p, f32p, vp, f32p, i32]
         L.vitb200_forward_u8.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32]
+        L.vitb200_forward_u8_async.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i32]
         L.vitb200_forward_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, vp]
         L.vitb200_last_launch_count.argtypes = [vp]
         L.vitb200_stream.argtypes = [vp]
