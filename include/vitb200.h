@@ -170,6 +170,16 @@ int vitb200_forward_debug(vitb200_engine *e, const float *images, int batch, flo
 int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint16_t *A, const uint16_t *W,
                       const float *bias, const float *resid, float *out);
 
+/* Prototype of the reference's q8_0 x q8_0 linear layer on the INTEGER tensor cores (tcgen05.mma kind::i8, one K = 32 MMA per
+ * q8_0 block; csrc/gemm_q8_tcgen05.cuh).  Replaces, for one layer, quantize_row_q8_0 (reference ggml-quants.c:702-790: the f32
+ * activation rows x [M][K] are quantised on the device, bit for bit as the reference does) + ggml_vec_dot_q8_0_q8_0
+ * (ggml-quants.c:3521+) + the bias add.  w_q8_0 is the tensor as stored in a q8_0 model file: [N][K/32] blocks of {f16 d; int8 q[32]}
+ * (ggml-quants.h:42-46).  y = float32 [M][N]; xq (int8 [M][K]) and xd (float32 [M][K/32]) optionally receive the quantised
+ * activations; with iters > 0 *ms_per_launch receives the CUDA-event time of one GEMM launch averaged over `iters` launches.
+ * K % 128 == 0, N % 4 == 0.  Not part of the forward schedule (it is slower than the f16 tensor-core path). */
+int vitb200_test_gemm_q8(int device, int M, int N, int K, const float *x, const void *w_q8_0, const float *bias, float *y,
+                         int8_t *xq, float *xd, int iters, float *ms_per_launch);
+
 /* Stand-alone run of one attention kernel (head dim 64) over a fused QKV buffer: qkv = f16 bits [B*N][3*H*64] (what the qkv
  * GEMM leaves behind, reference vit.cpp:826-846), out = float32 [B*N][H*64] (the merged heads before proj, vit.cpp:860-866).
  * kernel: 0 = the engine's choice for N, 1 = mma.sync two-pass, 2 = tcgen05 single block (N <= 224), 3 = tcgen05 two sweeps

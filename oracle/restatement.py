@@ -42,6 +42,7 @@ def lib():
         L.vo_softmax_rows.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.vo_layernorm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
         L.vo_set_threads.argtypes = [C.c_int]
+        L.vo_linear_q8_0.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -149,3 +150,19 @@ def layernorm(x, w, b, eps=1e-6):
     y = np.empty_like(x)
     lib().vo_layernorm(x.ctypes.data, x.shape[0], x.shape[1], w.ctypes.data, b.ctypes.data, eps, y.ctypes.data)
     return y
+
+
+def linear_q8_0(x, w_blocks, bias):
+    """One q8_0 linear layer with the reference's arithmetic: x [T][K] f32, w_blocks = uint8 [N][K/32][34] (block_q8_0 as stored
+    in a model file), bias [N].  Returns (y [T][N] f32, xq [T][K] int8, xd [T][K/32] f32 -- the quantised activation rows)."""
+    x = np.ascontiguousarray(x, np.float32)
+    w_blocks = np.ascontiguousarray(w_blocks, np.uint8)
+    bias = np.ascontiguousarray(bias, np.float32)
+    T, K = x.shape
+    N = bias.shape[0]
+    assert w_blocks.size == N * (K // 32) * 34
+    y = np.empty((T, N), np.float32)
+    xq = np.empty((T, K), np.int8)
+    xd = np.empty((T, K // 32), np.float32)
+    lib().vo_linear_q8_0(T, N, K, w_blocks.ctypes.data, bias.ctypes.data, x.ctypes.data, y.ctypes.data, xd.ctypes.data, xq.ctypes.data)
+    return y, xq, xd

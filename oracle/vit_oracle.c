@@ -97,7 +97,12 @@ static inline float reduce_4x8(const float *s) {
  * 5 = 1 + only q rounded; 6 = 1 + only k rounded; 7 = 1 + q,k,v replaced by hi + lo with hi = f16(x), lo = f16(x - hi) (what a
  * split-precision tensor-core attention sees); 8 = reference rounding points with every dot product accumulated in f32 in blocks
  * of 16 terms (each block summed exactly, then added to a running f32 sum: a tensor-core-like order).  Used to measure the parity noise floor between non-bit-identical
- * implementations and which attention operand's precision matters. */
+ * implementations and which attention operand's precision matters.
+ * q8_0 models only: 9 = each q8_0 dot product replaced by sum_k f16(d_w q_w) * f16(d_x q_x) accumulated in double -- what an f16
+ * tensor-core GEMM sees when the weights are dequantised once and the activations are quantised per 32-block exactly as the
+ * reference does (quantize_row_q8_0) and then folded back to f16; 10 = the same with the activation factor d_x q_x kept exact
+ * (a hi + lo f16 pair); 11 = dequantised f16 weights against plain f16-rounded activations, no activation quantisation (round 1's
+ * engine).  The rest of the graph keeps the reference's rounding points. */
 static int g_variant = 0;
 void vo_set_variant(int v) { g_variant = v; }
 
@@ -275,7 +280,19 @@ static void linear_rows(int o0, int o1, void *cv) {
     for (int o = o0; o < o1; ++o)
         for (int t = 0; t < T; ++t) {
             float v;
-            if (W->type == 8)
+            if (W->type == 8 && g_variant >= 9) {
+                const float *dw = W->qd + (size_t)o * (K / QK8_0), *dx = c->xd + (size_t)t * (K / QK8_0);
+                const int8_t *qw = W->qs + (size_t)o * K, *qx = c->xq + (size_t)t * K;
+                double acc = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    const float wv = round_f16(dw[k / QK8_0] * (float)qw[k]);
+                    float av = dx[k / QK8_0] * (float)qx[k];
+                    if (g_variant == 9) av = round_f16(av);
+                    if (g_variant == 11) av = round_f16(c->xa[(size_t)t * K + k]);
+                    acc += (double)wv * (double)av;
+                }
+                v = (float)acc;
+            } else if (W->type == 8)
                 v = dot_q8_0(K, W->qd + (size_t)o * (K / QK8_0), W->qs + (size_t)o * K,
                              c->xd + (size_t)t * (K / QK8_0), c->xq + (size_t)t * K);
             else
@@ -471,3 +488,16 @@ void vo_exp_table(const float *x, float *y, int64_t n) { init_tables(); for (int
 void vo_softmax_rows(float *p, int rows, int n) { init_tables(); for (int r = 0; r < rows; ++r) softmax_row(p + (size_t)r * n, n); }
 void vo_layernorm(const float *x, int T, int D, const float *w, const float *b, float eps, float *y) { layernorm(x, T, D, w, b, eps, y); }
 void vo_set_threads(int n) { g_threads = n; }
+/* Test helper for the q8_0 GEMM prototype: ONE q8_0 linear layer, y[T][N] = W x + b, exactly as the reference evaluates it
+ * (quantize_row_q8_0 on every activation row, then ggml_vec_dot_q8_0_q8_0 per output, ggml.c:9493-9506 + ggml-quants.c:702-790,
+ * 3521+).  wblocks = the tensor as stored in the model file ([N][K/32] block_q8_0).  xd_out [T][K/32] / xq_out [T][K] (optional)
+ * receive the quantised activations. */
+void vo_linear_q8_0(int T, int N, int K, const void *wblocks, const float *bias, const float *x, float *y, float *xd_out, int8_t *xq_out) {
+    vo_mat W;
+    mat_init(&W, wblocks, 8, N, K);
+    linear(&W, bias, x, T, y);
+    if (xd_out && xq_out)
+        for (int t = 0; t < T; ++t) quantize_row_q8_0(x + (size_t)t * K, K, xd_out + (size_t)t * (K / QK8_0), xq_out + (size_t)t * K);
+    mat_free(&W);
+}
+

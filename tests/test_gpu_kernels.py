@@ -157,3 +157,30 @@ def test_attention_kernels_against_numpy(B, N, H, kernel):
     err = np.abs(out - ref)
     tol = 2.0 ** -10 * np.abs(ref) + 2e-3 * np.abs(ref).max()
     assert (err <= tol).all(), (err.max(), np.abs(ref).max(), np.unravel_index(err.argmax(), err.shape))
+
+
+# ---- q8_0 linear layer on the integer tensor cores (prototype, BASELINE.json configs[4]) ---------------------------------------
+Q8_CASES = [(128, 128, 128), (1, 128, 128), (300, 576, 768), (197 * 3, 2304, 768), (197 * 2, 768, 3072), (129, 1000, 768), (640, 132, 256)]
+
+
+@pytest.mark.parametrize("M,N,K", Q8_CASES)
+def test_q8_0_gemm_matches_the_reference_integer_dot(M, N, K):
+    """tcgen05 kind::i8 GEMM + on-device activation quantisation against the oracle's quantize_row_q8_0 + vec_dot_q8_0_q8_0
+    (bit-exact restatements of the reference, tests/test_oracle.py): the quantised activations (integer work) must be bit-identical,
+    the f32 outputs within 1e-5 of the row's largest output (same products, same f32 accumulation, different order of the
+    reference's eight partial lanes)."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    x = (rng.standard_normal((M, K)) * rng.uniform(0.2, 3.0, (M, 1))).astype(np.float32)
+    x[0, :32] = 0.0                                  # an all-zero block: d = 0, id = 0 (ggml-quants.c:733)
+    if M > 2:
+        x[2, 5] = 1e4                                # an outlier squeezing the rest of its block to a few levels
+    w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
+    wb = pkg.convert.quantize_q8_0_reference(w.reshape(-1))  # the file quantiser (roundf variant), as `quantize` writes it
+    bias = rng.standard_normal(N).astype(np.float32)
+    y_ref, xq_ref, xd_ref = rs.linear_q8_0(x, wb, bias)
+    y, xq, xd, _ = eng.test_gemm_q8(x, wb, bias)
+    assert np.array_equal(xq, xq_ref), "quantised activations differ from quantize_row_q8_0"
+    assert np.array_equal(xd.view(np.uint32), xd_ref.view(np.uint32)), "block scales differ from quantize_row_q8_0"
+    scale = np.abs(y_ref).max(axis=1, keepdims=True)
+    err = (np.abs(y - y_ref) / scale).max()
+    assert err <= 1e-5, f"q8_0 GEMM error {err:.3e}"

@@ -10,9 +10,9 @@
   (timm `VisionTransformer` names, reference vit.cpp:518-579); the head count is not recoverable from shapes and defaults to
   hidden / 64 (true for every timm ViT the reference lists).
 * `quantize_model_file` restates reference quantize.cpp for q8_0 (every 2-D `*weight` tensor, quantize_row_q8_0_reference,
-  ggml-quants.c): byte-identical to the reference binary's output (tests/test_oracle.py).
+  ggml-quants.c): byte-identical to the reference binary's output (pinned by the CPU test-suite).
 
-Host-side tooling: nothing here touches the GPU or the oracle.
+Host-side tooling: nothing here touches the GPU or the test infrastructure.
 """
 from __future__ import annotations
 

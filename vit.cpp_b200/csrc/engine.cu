@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "attention_tcgen05.cuh"
 #include "attention_tcgen05_long.cuh"
+#include "gemm_q8_tcgen05.cuh"
 #include "gguf_file.hpp"
 #include "preprocess.cuh"
 
@@ -116,6 +117,22 @@ int make_tmap(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uin
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u", (int)r,
                                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch, box_rows);
+    return 0;
+}
+
+// generic 2-D row-major tensor map (the q8_0 prototype's int8 planes and f32 scale planes)
+int make_tmap_2d(CUtensorMap *m, CUtensorMapDataType dt, size_t elem_bytes, const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                 uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw)
+{
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * elem_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(2d) failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols);
     return 0;
 }
 
@@ -1523,6 +1540,95 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
     } while (0);
     cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dO); cudaFree(dR); cudaFree(dO2);
     return rc;
+}
+
+// q8_0 linear layer on the integer tensor cores (gemm_q8_tcgen05.cuh; prototype for BASELINE.json configs[4]): x [M][K] f32 is
+// quantised on the device exactly as the reference quantises activation rows, w is a q8_0 tensor in the model-file layout
+// ([N][K/32] blocks of {f16 d; int8 q[32]}, ggml-quants.h:42-46).  Outputs: y [M][N] f32, and (optional) the quantised activations
+// xq [M][K] int8, xd [M][K/32] f32.  iters > 0 additionally times `iters` back-to-back GEMM launches (CUDA events) into *ms_per_launch.
+int vitb200_test_gemm_q8(int device, int M, int N, int K, const float *x, const void *w_q8_0, const float *bias, float *y,
+                         int8_t *xq, float *xd, int iters, float *ms_per_launch)
+{
+    if (!x || !w_q8_0 || !bias || !y || M < 1 || N < 1 || K < 1) return fail("bad argument");
+    if (K % Q8_BK != 0) return fail("K must be a multiple of %d", Q8_BK);
+    if (N % 4 != 0) return fail("N must be a multiple of 4");
+    VB_NOEXCEPT_BEGIN
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: the vit.cpp_b200 forward path has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    const int KB = K / 32;
+    // repack the 34-byte blocks: int8 plane [N][K] + transposed scale plane [K/32][N]
+    std::vector<int8_t> wq((size_t)N * K);
+    std::vector<float> wdT((size_t)KB * N);
+    const uint8_t *blk = (const uint8_t *)w_q8_0;
+    for (int n = 0; n < N; ++n)
+        for (int b = 0; b < KB; ++b)
+        {
+            const uint8_t *src = blk + ((size_t)n * KB + b) * 34;
+            uint16_t du;
+            memcpy(&du, src, 2);
+            wdT[(size_t)b * N + n] = host_f16_to_f32(du);
+            memcpy(&wq[(size_t)n * K + (size_t)b * 32], src + 2, 32);
+        }
+    float *dX = nullptr, *dAd = nullptr, *dWd = nullptr, *dB = nullptr, *dY = nullptr;
+    int8_t *dAq = nullptr, *dWq = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 1;
+    do
+    {
+        if (cudaMalloc(&dX, (size_t)M * K * 4) || cudaMalloc(&dAq, (size_t)M * K) || cudaMalloc(&dAd, (size_t)M * KB * 4) ||
+            cudaMalloc(&dWq, (size_t)N * K) || cudaMalloc(&dWd, (size_t)KB * N * 4) || cudaMalloc(&dB, (size_t)N * 4) ||
+            cudaMalloc(&dY, (size_t)M * N * 4)) { fail("cudaMalloc failed"); break; }
+        cudaMemcpy(dX, x, (size_t)M * K * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dWq, wq.data(), wq.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(dWd, wdT.data(), wdT.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice);
+        cudaMemset(dY, 0, (size_t)M * N * 4);
+        CUtensorMap tA, tW, tAd, tWd;
+        if (make_tmap_2d(&tA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dAq, (uint64_t)M, (uint64_t)K, (uint64_t)K, Q8_BK, Q8_BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dWq, (uint64_t)N, (uint64_t)K, (uint64_t)K, Q8_BK, Q8_BN, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            make_tmap_2d(&tAd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dAd, (uint64_t)M, (uint64_t)KB, (uint64_t)KB, 4, Q8_BM, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+            make_tmap_2d(&tWd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dWd, (uint64_t)KB, (uint64_t)N, (uint64_t)N, Q8_BN, 4, CU_TENSOR_MAP_SWIZZLE_NONE))
+            break;
+        const long long n_blocks = (long long)M * KB;
+        const int qthreads = 256;
+        const long long qgrid = (n_blocks * 8 + qthreads - 1) / qthreads;
+        quantize_q8_0_kernel<<<(unsigned)qgrid, qthreads>>>(dX, dAq, dAd, n_blocks);
+        if (cudaGetLastError() != cudaSuccess) { fail("quantize launch failed"); break; }
+        if (cudaFuncSetAttribute(gemm_q8_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q8_SMEM_BYTES) != cudaSuccess) { fail("cudaFuncSetAttribute failed"); break; }
+        Q8GemmParams p{};
+        p.M = M; p.N = N; p.K = K; p.bias = dB; p.out = dY; p.ldo = N;
+        const int tiles = ((M + Q8_BM - 1) / Q8_BM) * ((N + Q8_BN - 1) / Q8_BN);
+        const int grid = tiles < prop.multiProcessorCount ? tiles : prop.multiProcessorCount;
+        gemm_q8_tcgen05_kernel<<<grid, Q8_THREADS, Q8_SMEM_BYTES>>>(tA, tW, tAd, tWd, p);
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { fail("q8_0 GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
+        cudaMemcpy(y, dY, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+        if (xq) cudaMemcpy(xq, dAq, (size_t)M * K, cudaMemcpyDeviceToHost);
+        if (xd) cudaMemcpy(xd, dAd, (size_t)M * KB * 4, cudaMemcpyDeviceToHost);
+        if (iters > 0 && ms_per_launch)
+        {
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0);
+            for (int i = 0; i < iters; ++i) gemm_q8_tcgen05_kernel<<<grid, Q8_THREADS, Q8_SMEM_BYTES>>>(tA, tW, tAd, tWd, p);
+            cudaEventRecord(e1);
+            err = cudaDeviceSynchronize();
+            if (err != cudaSuccess) { fail("q8_0 GEMM kernel failed: %s", cudaGetErrorString(err)); break; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            *ms_per_launch = ms / (float)iters;
+        }
+        rc = 0;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(dX); cudaFree(dAq); cudaFree(dAd); cudaFree(dWq); cudaFree(dWd); cudaFree(dB); cudaFree(dY);
+    return rc;
+    VB_NOEXCEPT_END((void)0)
 }
 
 } // extern "C"

@@ -83,6 +83,7 @@ def lib():
         L.vitb200_forward_debug.argtypes = [vp, f32p, i32, f32p, f32p, C.POINTER(Taps)]
         L.vitb200_test_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         L.vitb200_test_dequant.argtypes = [i32, vp, C.c_int64, vp]
+        L.vitb200_test_gemm_q8.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
         L.vitb200_test_attention.argtypes = [i32, i32, i32, i32, i32, vp, vp]
         L.vitb200_test_attention_hilo.argtypes = [i32, i32, i32, i32, vp, vp, vp]
         _lib = L
@@ -305,3 +306,22 @@ def test_gemm(M: int, N: int, K: int, epilogue: int, A16: np.ndarray, W16: np.nd
     _check(lib().vitb200_test_gemm(device, M, N, K, epilogue, A.ctypes.data, W.ctypes.data, b.ctypes.data,
                                    r.ctypes.data if r is not None else None, out.ctypes.data), "vitb200_test_gemm")
     return out
+
+
+def test_gemm_q8(x, w_blocks, bias, device: int = 0, iters: int = 0):
+    """The q8_0 linear layer on the integer tensor cores (vitb200_test_gemm_q8): x float32 [M][K], w_blocks = uint8 bytes of a q8_0
+    tensor [N][K/32] blocks (model-file layout), bias [N].  Returns (y [M][N] f32, xq [M][K] int8, xd [M][K/32] f32, ms per launch or None)."""
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w_blocks, np.uint8)
+    b = np.ascontiguousarray(bias, np.float32)
+    M, K = x.shape
+    N = b.shape[0]
+    if w.size != N * (K // 32) * 34:
+        raise ValueError("w_blocks does not hold N * K / 32 q8_0 blocks")
+    y = np.empty((M, N), np.float32)
+    xq = np.empty((M, K), np.int8)
+    xd = np.empty((M, K // 32), np.float32)
+    ms = C.c_float(0.0)
+    _check(lib().vitb200_test_gemm_q8(device, M, N, K, x.ctypes.data, w.ctypes.data, b.ctypes.data, y.ctypes.data, xq.ctypes.data,
+                                      xd.ctypes.data, iters, C.cast(C.pointer(ms), C.c_void_p)), "vitb200_test_gemm_q8")
+    return y, xq, xd, (ms.value if iters > 0 else None)
