@@ -104,6 +104,12 @@ int vitb200_sync(vitb200_engine *e);
  * as long as every shard fits. */
 int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs, float *logits,
                             int32_t *topk_idx, float *topk_prob, int k);
+/* Pipelined form: returns once every shard is enqueued on its engine's two-slot pipeline (vitb200_forward_async), so the same host
+ * thread can submit the next global batch while this one runs; buffers must stay valid until vitb200_sync_all() (== vitb200_sync
+ * on every engine) returns.  vitb200_forward_sharded == this + vitb200_sync_all. */
+int vitb200_forward_sharded_async(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs,
+                                  float *logits, int32_t *topk_idx, float *topk_prob, int k);
+int vitb200_sync_all(vitb200_engine *const *engines, int n_engines);
 
 /* vit_image_preprocess + vit_predict fused on the GPU (reference vit.h:119, vit.cpp:130-305 + vit.cpp:1004): `images[b]` is the
  * interleaved RGB u8 image the reference's load_image_from_file produces (image_u8::data, vit.h:91-96), nx[b] x ny[b]

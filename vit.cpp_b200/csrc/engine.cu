@@ -1317,8 +1317,8 @@ static int forward_host(vitb200_engine *e, const float *images, int batch, float
 // Data-parallel forward over several engines (one per GPU, weights replicated) driven from ONE host thread: image b goes to
 // engine floor(b * n / batch)-style contiguous shards, every shard is enqueued with the non-blocking pipeline entry point, then
 // all engines are synchronised.  No collective: shards are independent.
-int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs, float *logits,
-                            int32_t *topk_idx, float *topk_prob, int k)
+static int forward_sharded_impl(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs, float *logits,
+                                int32_t *topk_idx, float *topk_prob, int k, bool sync)
 {
     if (!engines || n_engines < 1 || !images) return fail("null argument");
     const vitb200_engine *e0 = engines[0];
@@ -1361,6 +1361,30 @@ int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const
         }
         begin += cnt;
     }
+    if (!sync) return 0;
+    int rc = 0;
+    for (int g = 0; g < n_engines; ++g)
+        if (engines[g] && vitb200_sync(engines[g])) rc = 1;
+    return rc;
+}
+
+int vitb200_forward_sharded(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs, float *logits,
+                            int32_t *topk_idx, float *topk_prob, int k)
+{
+    return forward_sharded_impl(engines, n_engines, images, batch, probs, logits, topk_idx, topk_prob, k, true);
+}
+
+// Pipelined form: every shard goes through its engine's two-slot vitb200_forward_async pipeline and the call returns; the host
+// thread can enqueue the next global batch (other host buffers) while this one runs.  vitb200_sync_all() waits for everything.
+int vitb200_forward_sharded_async(vitb200_engine *const *engines, int n_engines, const float *images, int batch, float *probs,
+                                  float *logits, int32_t *topk_idx, float *topk_prob, int k)
+{
+    return forward_sharded_impl(engines, n_engines, images, batch, probs, logits, topk_idx, topk_prob, k, false);
+}
+
+int vitb200_sync_all(vitb200_engine *const *engines, int n_engines)
+{
+    if (!engines || n_engines < 1) return fail("null argument");
     int rc = 0;
     for (int g = 0; g < n_engines; ++g)
         if (engines[g] && vitb200_sync(engines[g])) rc = 1;
