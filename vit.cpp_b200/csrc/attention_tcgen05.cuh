@@ -322,8 +322,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const int n_full = p.N >> 5; // chunks with all 32 keys valid
                     float l0 = 0.f, l1 = 0.f, l2s = 0.f, l3 = 0.f;
                     int c = 0;
-                    // (a software-pipelined variant -- the next chunk's tcgen05.ld in flight during the exponentials -- needs ~20 more
-                    // registers than the 168 a 10-warp CTA gets; it spilled inside this loop and ran 1.7x slower: measured, dropped)
+                    // (software-pipelined variants -- the next chunk's tcgen05.ld in flight during the exponentials -- were measured twice and
+                    // dropped: with 64-column buffers at 168 registers the loop spilled (1.7x slower); with 32-column buffers and no spills, in
+                    // this 10-warp layout or in a 12-warp layout whose soft-max warpgroups take 224 registers through setmaxnreg, the pass
+                    // got 8 % SLOWER (1.76 -> 1.87-1.91 ms per forward): the other soft-max warp of the sub-partition already covers the
+                    // TMEM round trip, and the 64-column steps give the scheduler more independent work; profiles/microbench_r02.md)
 #pragma unroll 1 // (ptxas otherwise unrolls x4 with three peeled copies: 213 KB of SASS, the live part no longer fits the instruction cache)
                     for (; c + 2 <= n_full; c += 2)
                     {
