@@ -703,42 +703,77 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int part = 0; part < (kHiLo ? 2 : 1); ++part)
                     {
-                    if (lane == 0) ptx::tma_store_wait_read<0>(); // the previous box has left the staging buffer
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) // 8 chunks of 8 columns (16 B of f16)
+                    if constexpr (EPI == EPI_BIAS_GELU_F16)
                     {
-                        uint32_t packed[4];
-                        // the strip holds zeros for columns >= N (N % 8 == 0 for f16 outputs: a chunk of 8 columns is all-in or all-out)
-                        const float4 bl = bias_s4[(cp >> 1) * 16 + j * 2], bh = bias_s4[(cp >> 1) * 16 + j * 2 + 1];
-                        const float bias8[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+                        // GELU: all the arithmetic of the box first, into registers; only then wait for the previous TMA store to have read
+                        // the staging box and copy the packed rows in -- the store's shared-memory read overlaps the (long) GELU chain
+                        // instead of preceding it.  A/B at batch 256: fc1 2.60 -> 2.46 ms per forward; the same reordering makes the
+                        // hi-lo epilogue SLOWER (qkv 2.16 -> 2.33 ms: 160 instead of 124 registers, both parts' packed rows live), so
+                        // that one keeps the wait-first order below (profiles/microbench_r02.md).
+                        uint32_t packed[32];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
+                        for (int j = 0; j < 8; ++j) // 8 chunks of 8 columns (16 B of f16)
                         {
-                            float x0, x1; // acc + bias, both lanes in one FADD2
-                            ptx::unpack_f32x2(ptx::add_f32x2(ptx::pack_f32x2(__uint_as_float(v[j * 8 + e * 2]), __uint_as_float(v[j * 8 + e * 2 + 1])),
-                                                             ptx::pack_f32x2(bias8[e * 2], bias8[e * 2 + 1])), x0, x1);
-                            __half2 h;
-                            if constexpr (EPI == EPI_BIAS_GELU_F16)
+                            const float4 bl = bias_s4[(cp >> 1) * 16 + j * 2], bh = bias_s4[(cp >> 1) * 16 + j * 2 + 1];
+                            const float bias8[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
                             {
-                                // ggml.c:1434-1441: y = f16(gelu(f32(f16(x))))
-                                const float2 r = __half22float2(__floats2half2_rn(x0, x1));
+                                float x0, x1; // acc + bias, both lanes in one FADD2
+                                ptx::unpack_f32x2(ptx::add_f32x2(ptx::pack_f32x2(__uint_as_float(v[j * 8 + e * 2]), __uint_as_float(v[j * 8 + e * 2 + 1])),
+                                                                 ptx::pack_f32x2(bias8[e * 2], bias8[e * 2 + 1])), x0, x1);
+                                const float2 r = __half22float2(__floats2half2_rn(x0, x1)); // ggml.c:1434-1441: y = f16(gelu(f32(f16(x))))
                                 float g0, g1;
                                 gelu_tanh_f32x2(r.x, r.y, g0, g1);
-                                h = __floats2half2_rn(g0, g1);
+                                const __half2 h = __floats2half2_rn(g0, g1);
+                                packed[j * 4 + e] = *reinterpret_cast<const uint32_t *>(&h);
                             }
-                            else
-                            {
-                                h = __floats2half2_rn(x0, x1);
-                                if (kHiLo && part == 1)
-                                {
-                                    const float2 hf = __half22float2(h);
-                                    h = __floats2half2_rn(__fsub_rn(x0, hf.x), __fsub_rn(x1, hf.y));
-                                }
-                            }
-                            packed[e] = *reinterpret_cast<uint32_t *>(&h);
                         }
-                        ptx::st_shared_v4(stg_u32 + (uint32_t)lane * 128u + (uint32_t)((j ^ sw) << 4), packed[0], packed[1], packed[2], packed[3]);
+                        if (lane == 0) ptx::tma_store_wait_read<0>(); // the previous box has left the staging buffer
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            ptx::st_shared_v4(stg_u32 + (uint32_t)lane * 128u + (uint32_t)((j ^ sw) << 4), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                    else
+                    {
+                        if (lane == 0) ptx::tma_store_wait_read<0>(); // the previous box has left the staging buffer
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) // 8 chunks of 8 columns (16 B of f16)
+                        {
+                            uint32_t packed[4];
+                            // the strip holds zeros for columns >= N (N % 8 == 0 for f16 outputs: a chunk of 8 columns is all-in or all-out)
+                            const float4 bl = bias_s4[(cp >> 1) * 16 + j * 2], bh = bias_s4[(cp >> 1) * 16 + j * 2 + 1];
+                            const float bias8[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                            {
+                                float x0, x1; // acc + bias, both lanes in one FADD2
+                                ptx::unpack_f32x2(ptx::add_f32x2(ptx::pack_f32x2(__uint_as_float(v[j * 8 + e * 2]), __uint_as_float(v[j * 8 + e * 2 + 1])),
+                                                                 ptx::pack_f32x2(bias8[e * 2], bias8[e * 2 + 1])), x0, x1);
+                                __half2 h;
+                                if constexpr (EPI == EPI_BIAS_GELU_F16)
+                                {
+                                    // ggml.c:1434-1441: y = f16(gelu(f32(f16(x))))
+                                    const float2 r = __half22float2(__floats2half2_rn(x0, x1));
+                                    float g0, g1;
+                                    gelu_tanh_f32x2(r.x, r.y, g0, g1);
+                                    h = __floats2half2_rn(g0, g1);
+                                }
+                                else
+                                {
+                                    h = __floats2half2_rn(x0, x1);
+                                    if (kHiLo && part == 1)
+                                    {
+                                        const float2 hf = __half22float2(h);
+                                        h = __floats2half2_rn(__fsub_rn(x0, hf.x), __fsub_rn(x1, hf.y));
+                                    }
+                                }
+                                packed[e] = *reinterpret_cast<uint32_t *>(&h);
+                            }
+                            ptx::st_shared_v4(stg_u32 + (uint32_t)lane * 128u + (uint32_t)((j ^ sw) << 4), packed[0], packed[1], packed[2], packed[3]);
+                        }
                     }
                     ptx::fence_proxy_async_smem(); // generic-proxy writes -> visible to the TMA store (async proxy)
                     __syncwarp();
