@@ -449,6 +449,15 @@ def test_in_process_sharding_over_all_visible_gpus():
     p2, i2, v2 = eng.vit_predict(models[-1], imgs[4:], 5)
     assert np.array_equal(idx[4:], i2)
     np.testing.assert_allclose(probs[4:], p2, rtol=0, atol=1e-6)
+    # pipelined form: two global batches in flight from one host thread, then one wait for everything
+    imgs2 = gf.synthetic_images(7, models[0].img_size, seed=7)
+    outs = [(np.empty((7, models[0].num_classes), np.float32), np.empty((7, 5), np.int32), np.empty((7, 5), np.float32)) for _ in range(2)]
+    eng.vit_predict_sharded_async(models, imgs, *outs[0])
+    eng.vit_predict_sharded_async(models, imgs2, *outs[1])
+    eng.sync_all(models)
+    assert np.array_equal(outs[0][0], probs) and np.array_equal(outs[0][1], idx)
+    pb, ib, vb = eng.vit_predict_sharded(models, imgs2, 5)
+    assert np.array_equal(outs[1][0], pb) and np.array_equal(outs[1][1], ib) and np.array_equal(outs[1][2], vb)
     for m in models:
         m.close()
 

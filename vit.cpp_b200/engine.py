@@ -212,6 +212,30 @@ def vit_predict_sharded(models, images: np.ndarray, topk: int = 5):
     return probs, idx, val
 
 
+def vit_predict_sharded_async(models, images: np.ndarray, probs: np.ndarray, idx: np.ndarray, val: np.ndarray):
+    """Pipelined vit_predict_sharded (vitb200_forward_sharded_async): enqueues the global batch over the engines and returns; the
+    caller-owned `images` / output arrays (C-contiguous, shapes as vit_predict_sharded returns them) must stay alive and untouched
+    until sync_all(models).  Lets one host thread keep several global batches in flight (two pipeline slots per engine)."""
+    B = images.shape[0]
+    if images.dtype != np.float32 or not images.flags.c_contiguous:
+        raise ValueError("images must be a C-contiguous float32 array")
+    for a, dt in ((probs, np.float32), (idx, np.int32), (val, np.float32)):
+        if a.dtype != dt or not a.flags.c_contiguous or a.shape[0] != B:
+            raise ValueError("output arrays must be C-contiguous, one leading row per image")
+    hs = (C.c_void_p * len(models))(*[m.handle for m in models])
+    L = lib()
+    L.vitb200_forward_sharded_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    _check(L.vitb200_forward_sharded_async(hs, len(models), images.ctypes.data, B, probs.ctypes.data, None, idx.ctypes.data,
+                                           val.ctypes.data, idx.shape[-1]), "vit_predict_sharded_async")
+
+
+def sync_all(models):
+    hs = (C.c_void_p * len(models))(*[m.handle for m in models])
+    L = lib()
+    L.vitb200_sync_all.argtypes = [C.c_void_p, C.c_int]
+    _check(L.vitb200_sync_all(hs, len(models)), "vitb200_sync_all")
+
+
 def vit_image_preprocess_predict(model: VitModel, images_u8, bilinear: bool = False, topk: int = 5, predict: bool = True):
     """reference vit_image_preprocess (vit.cpp:289) + vit_predict on the GPU for a list of HxWx3 uint8 RGB arrays of any size.
     Returns (image_f32 batch [B,S,S,3], probs, topk_idx, topk_prob, logits); the last four are None if predict is False."""
