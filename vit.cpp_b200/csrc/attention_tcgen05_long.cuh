@@ -33,8 +33,10 @@ struct AttnLongParams
     int nb;          // key blocks (even, 4..ATT_LONG_MAX_BLOCKS) of <= 96 keys
     int key0[9];     // first key of block j (att_long_block_key0), key0[nb] = NKP: read from the constant bank, no divisions on the device
     float scale;     // 1/sqrt(64)
+    long long *trace; // dev only (VITB200_ATTN_TRACE): clock64 stamps of CTA 0, [tile < 16][slot < 32] (warpgroup w writes slots 8 w ..); NULL in production
 };
 
+#define ATT_LONG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && tile_seq < 16 && q == 0 && lane == 0) p.trace[tile_seq * 32 + 8 * w + (slot)] = clock64(); } while (0)
 
 constexpr int ATT_LONG_BUF_COLS = 96, ATT_LONG_OCOL = 384, ATT_LONG_MAX_BLOCKS = 8, ATT_LONG_MAX_KEYS = 640;
 
@@ -246,12 +248,14 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t t_o = t_lane + ATT_LONG_OCOL;
         uint32_t c_sfull[2] = {0, 0}, c_ofull = 0; // s_full parity of this warpgroup's two buffers
+        int tile_seq = 0; // tiles this CTA has processed (trace index)
         for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x)
         {
             const int b = prob / p.H, h = prob - b * p.H;
-            for (int ti = 0; ti < p.n_tiles; ++ti)
+            for (int ti = 0; ti < p.n_tiles; ++ti, ++tile_seq)
             {
                 const bool warp_valid = (ti * 128 + q * 32) < p.N; // warp owns at least one real query row
+                ATT_LONG_TRACE(0);
                 // ---- sweep A: true row maximum over the valid keys (ggml.c:10533-10534), this warpgroup's blocks
                 float mx = -INFINITY;
                 for (int j = w; j < nb; j += 2)
@@ -298,10 +302,13 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(s_free(bb));
                 }
+                ATT_LONG_TRACE(1);
                 mx_ex[w * 128 + row_in_tile] = mx;
                 ptx::named_bar_sync(1, 256);
+                ATT_LONG_TRACE(2);
                 mx = fmaxf(mx_ex[row_in_tile], mx_ex[128 + row_in_tile]);
                 const float mxs = mx * p.scale; // ggml_scale_inplace (vit.cpp:851-854); exact, scale = 1/8
+                const uint64_t scale2 = ptx::pack_f32x2(p.scale, p.scale), nmax2 = ptx::pack_f32x2(-mxs, -mxs);
 
                 // ---- sweep B: P = f16(exp(f16(s*scale - max))) over S in place, l = sum P
                 float l0 = 0.f, l1 = 0.f, l2s = 0.f, l3 = 0.f;
@@ -315,39 +322,51 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     if (warp_valid)
                     {
                         const int valid = p.N - key0 < kb ? p.N - key0 : kb;
-                        // 16-key granules, one ahead: granule g+1 streams out of TMEM while granule g goes through the exp pipeline
-                        // (8 independent pairs, four partial sums).  Small granules keep the live registers under the 168 this
-                        // 10-warp CTA allows -- 32-key chunks spilled the partial sums into the dependency chain.
-                        const int ng = kb >> 4, gf = valid >> 4; // granules in the block / granules with all 16 keys valid
-                        uint32_t va[16], vb[16], pe[8];
-                        auto exp_granule = [&](const uint32_t(&v)[16]) {
-                            pe[0] = att_exp_pair(__fmaf_rn(__uint_as_float(v[0]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[1]), p.scale, -mxs), l0);
-                            pe[1] = att_exp_pair(__fmaf_rn(__uint_as_float(v[2]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[3]), p.scale, -mxs), l1);
-                            pe[2] = att_exp_pair(__fmaf_rn(__uint_as_float(v[4]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[5]), p.scale, -mxs), l2s);
-                            pe[3] = att_exp_pair(__fmaf_rn(__uint_as_float(v[6]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[7]), p.scale, -mxs), l3);
-                            pe[4] = att_exp_pair(__fmaf_rn(__uint_as_float(v[8]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[9]), p.scale, -mxs), l0);
-                            pe[5] = att_exp_pair(__fmaf_rn(__uint_as_float(v[10]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[11]), p.scale, -mxs), l1);
-                            pe[6] = att_exp_pair(__fmaf_rn(__uint_as_float(v[12]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[13]), p.scale, -mxs), l2s);
-                            pe[7] = att_exp_pair(__fmaf_rn(__uint_as_float(v[14]), p.scale, -mxs), __fmaf_rn(__uint_as_float(v[15]), p.scale, -mxs), l3);
-                        };
-                        int g = 0;
-                        if (gf > 0) ptx::tcgen05_ld_32x32b_x16(t_s, va);
-                        for (; g < gf; g += 2)
+                        // Mask-free 32-key chunks two at a time (two tcgen05.ld.x32, one wait, 64 exponentials with packed FP32 scale / shift /
+                        // log2(e), four partial sums) -- the single-block kernel's loop.  The first version here went 16 keys at a time with
+                        // the next granule's load in flight; the phase trace (tools/attn_long_trace.py) had it at 26-29 clocks per key
+                        // against 18 for this form: per warp the TMEM round trip is already covered by the other soft-max warp of the
+                        // sub-partition, and short steps only add waits and stores (same finding as profiles/microbench_r02.md).
+                        const int ng = kb >> 4, nc32 = valid >> 5; // 16-key granules in the block / chunks with all 32 keys valid
+                        int c = 0;
+#pragma unroll 1
+                        for (; c + 2 <= nc32; c += 2)
                         {
+                            uint32_t va[32], vb[32], pa[16], pb[16];
+                            ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, va);
+                            ptx::tcgen05_ld_32x32b_x32(t_s + c * 32 + 32, vb);
                             ptx::tcgen05_wait_ld();
-                            if (g + 1 < gf) ptx::tcgen05_ld_32x32b_x16(t_s + (g + 1) * 16, vb);
-                            exp_granule(va);
-                            ptx::tcgen05_st_32x32b_x8(t_s + g * 8, pe);
-                            if (g + 1 < gf)
+#pragma unroll
+                            for (int x = 0; x < 16; x += 2)
                             {
-                                ptx::tcgen05_wait_ld();
-                                if (g + 2 < gf) ptx::tcgen05_ld_32x32b_x16(t_s + (g + 2) * 16, va);
-                                exp_granule(vb);
-                                ptx::tcgen05_st_32x32b_x8(t_s + (g + 1) * 8, pe);
+                                pa[x] = att_exp_pair_raw(va[2 * x], va[2 * x + 1], scale2, nmax2, l0);
+                                pb[x] = att_exp_pair_raw(vb[2 * x], vb[2 * x + 1], scale2, nmax2, l1);
+                                pa[x + 1] = att_exp_pair_raw(va[2 * x + 2], va[2 * x + 3], scale2, nmax2, l2s);
+                                pb[x + 1] = att_exp_pair_raw(vb[2 * x + 2], vb[2 * x + 3], scale2, nmax2, l3);
                             }
+                            ptx::tcgen05_st_32x32b_x16(t_s + c * 16, pa);
+                            ptx::tcgen05_st_32x32b_x16(t_s + c * 16 + 16, pb);
                         }
+#pragma unroll 1
+                        for (; c < nc32; ++c)
+                        {
+                            uint32_t va[32], pa[16];
+                            ptx::tcgen05_ld_32x32b_x32(t_s + c * 32, va);
+                            ptx::tcgen05_wait_ld();
+#pragma unroll
+                            for (int x = 0; x < 16; x += 4)
+                            {
+                                pa[x] = att_exp_pair_raw(va[2 * x], va[2 * x + 1], scale2, nmax2, l0);
+                                pa[x + 1] = att_exp_pair_raw(va[2 * x + 2], va[2 * x + 3], scale2, nmax2, l1);
+                                pa[x + 2] = att_exp_pair_raw(va[2 * x + 4], va[2 * x + 5], scale2, nmax2, l2s);
+                                pa[x + 3] = att_exp_pair_raw(va[2 * x + 6], va[2 * x + 7], scale2, nmax2, l3);
+                            }
+                            ptx::tcgen05_st_32x32b_x16(t_s + c * 16, pa);
+                        }
+                        uint32_t va[16], pe[8];
+                        int g = 0;
                         // the granule straddling N (keys >= N get exactly zero) and the all-padding granules behind it
-                        for (g = gf; g < ng; ++g)
+                        for (g = nc32 * 2; g < ng; ++g)
                         {
                             const int col = g * 16;
                             if (col < valid)
@@ -377,9 +396,12 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     ptx::tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(p_ready(bb));
+                    if (p.trace && blockIdx.x == 0 && tile_seq < 16 && q == 0 && lane == 0 && (j >> 1) < 4) p.trace[tile_seq * 32 + 16 + 4 * w + (j >> 1)] = clock64();
                 }
+                ATT_LONG_TRACE(3);
                 l_ex[w * 128 + row_in_tile] = (l0 + l1) + (l2s + l3);
                 ptx::named_bar_sync(2, 256);
+                ATT_LONG_TRACE(4);
 
                 // ---- O = P V is complete: warpgroup 0 drains, releases, normalises and stores
                 if (w == 0)
@@ -387,6 +409,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     const float lsum = l_ex[row_in_tile] + l_ex[128 + row_in_tile];
                     ptx::mbar_wait(o_full, c_ofull++ & 1);
                     ptx::tcgen05_fence_after();
+                    ATT_LONG_TRACE(5);
                     uint32_t o[64];
                     if (warp_valid)
                     {
@@ -425,6 +448,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                             ptx::tma_store_commit();
                         }
                     }
+                    ATT_LONG_TRACE(6);
                 }
             }
         }

@@ -668,7 +668,30 @@ int launch_attention_tc_long(vitb200_engine *e, int B, cudaStream_t s)
         smem_set[dev & 63] = smem;
     }
     const int grid = p.n_problems < e->num_sms ? p.n_problems : e->num_sms;
+    // dev knob: VITB200_ATTN_TRACE=<file> dumps the clock64 phase stamps of CTA 0 (first 16 query tiles) of the first launch of the process
+    static int trace_state = 0; // 0 unknown, 1 armed, 2 done/off
+    if (trace_state == 0) trace_state = getenv("VITB200_ATTN_TRACE") ? 1 : 2;
+    long long *d_trace = nullptr;
+    if (trace_state == 1)
+    {
+        CUDA_TRY(cudaMalloc(&d_trace, 16 * 32 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(d_trace, 0, 16 * 32 * sizeof(long long)));
+        p.trace = d_trace;
+    }
     CUDA_TRY(launch_pdl(attention_tc_long_kernel, dim3(grid), dim3(ATT_LONG_THREADS), (size_t)smem, s, e->tmQ, e->tmKV64, e->tmAO, p));
+    if (d_trace)
+    {
+        std::vector<long long> h(16 * 32);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        if (FILE *f = fopen(getenv("VITB200_ATTN_TRACE"), "w"))
+        {
+            for (int i = 0; i < 16; ++i) { for (int j = 0; j < 32; ++j) fprintf(f, "%lld ", h[i * 32 + j]); fprintf(f, "\n"); }
+            fclose(f);
+        }
+        trace_state = 2;
+    }
     e->launches++;
     return 0;
 }
