@@ -29,3 +29,20 @@ for N, H, k in ((577, 2, eng.ATTN_TC_LONG), (225, 1, eng.ATTN_TC_LONG), (577, 1,
     out = eng.test_attention(qkv, 2, N, H, k)
     assert np.isfinite(out).all()
     print("attention", N, H, k, "ok")
+# round 2: the split-precision attention entry point, the hi-lo GEMM epilogue, the q8_0 integer tensor-core prototype
+N, H = 197, 2
+x = rng.normal(0, 1, (2 * N, 3 * H * 64)).astype(np.float32)
+out = eng.test_attention_hilo(x, 2, N, H)
+assert np.isfinite(out).all()
+print("attention hi-lo ok")
+A = rng.normal(0, 1, (300, 192)).astype(np.float16)
+W = rng.normal(0, 0.05, (576, 192)).astype(np.float16)
+for epi in (0, 1, 2, 4, 6):
+    out = eng.test_gemm(300, 576, 192, epi, A, W, np.zeros(576, np.float32), resid=np.zeros((300, 576), np.float32) if epi == 2 else None)
+    assert np.isfinite(out).all()
+print("gemm epilogues ok")
+xq = rng.normal(0, 1, (300, 256)).astype(np.float32)
+wb = pkg.convert.quantize_q8_0_reference((rng.normal(0, 0.05, (132, 256))).astype(np.float32).reshape(-1))
+y, _, _, _ = eng.test_gemm_q8(xq, wb, np.zeros(132, np.float32))
+assert np.isfinite(y).all()
+print("q8_0 gemm ok")
