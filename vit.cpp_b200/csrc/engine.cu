@@ -650,15 +650,15 @@ int launch_attention_tc_long(vitb200_engine *e, int B, cudaStream_t s)
     {
         const int chunks = (p.NKP + 31) / 32;    // 32-key chunks; a block holds at most 3 (96 TMEM columns)
         p.nb = (chunks + 2) / 3;
-        if (p.nb < 4) p.nb = 4;
-        p.nb += p.nb & 1;                        // even: the two warpgroups alternate blocks
+        if (p.nb < 2) p.nb = 2;                  // the sweep-B pipeline alternates between two buffers
     }
     p.scale = 1.0f / sqrtf((float)(p.D / p.H));
     if (p.nb > ATT_LONG_MAX_BLOCKS || (p.NKP + 31) / 32 < p.nb)
-        return fail("attention: %d tokens cannot be cut into 4..%d key blocks", e->N, ATT_LONG_MAX_BLOCKS);
+        return fail("attention: %d tokens cannot be cut into 2..%d key blocks", e->N, ATT_LONG_MAX_BLOCKS);
     for (int j = 0; j < p.nb; ++j) p.key0[j] = att_long_block_key0(p.NKP, p.nb, j);
     p.key0[p.nb] = p.NKP;
-    const int smem = 1024 + 2 * p.kv_rows * 128 + 2 * 16384 + 4 * 4096 + 2048 + 256;
+    if (p.n_tiles < 2) return fail("two-sweep attention needs at least two query tiles (N > 128)");
+    const int smem = attention_tc_long_smem_bytes(p.kv_rows);
     static int smem_set[64] = {};
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -1230,7 +1230,7 @@ static int test_attention_impl(int device, int kernel, int B, int N, int H, cons
     }
     if (kernel == 0) kernel = N <= 224 ? 2 : (N <= ATT_LONG_MAX_KEYS ? 3 : 1);
     if (kernel == 2 && N > 224) return bail(fail("tcgen05 single-block attention needs N <= 224"));
-    if (kernel == 3 && (N <= 112 || N > ATT_LONG_MAX_KEYS)) return bail(fail("tcgen05 two-sweep attention needs 112 < N <= %d", ATT_LONG_MAX_KEYS));
+    if (kernel == 3 && (N <= 128 || N > ATT_LONG_MAX_KEYS)) return bail(fail("tcgen05 two-sweep attention needs 128 < N <= %d", ATT_LONG_MAX_KEYS));
     e->attn_tc = kernel == 2;
     e->attn_tc_long = kernel == 3;
     if (kernel >= 2)
