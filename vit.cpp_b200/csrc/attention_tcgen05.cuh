@@ -16,8 +16,8 @@
 //   O = P V        tcgen05.mma TS: A = P from TMEM, B = V (NKP x 64, MN-major, same TMA tile), D in TMEM; O * (1/l) -> f16,
 //                  staged in shared memory (SWIZZLE_128B) and written with one TMA store per warp
 //
-// Q, K, V are read straight out of the [tokens][3*D] QKV buffer by TMA (column offset h*64 / D + h*64 / 2D + h*64): no
-// split / transpose copies.  Persistent CTAs (1 per SM), 10 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9
+// Q, K, V are read by TMA out of the HEAD-MAJOR QKV buffers the qkv GEMM's epilogue writes ([3 H planes][tokens][64]: plane h / H + h /
+// 2 H + h; every operand tile is one contiguous run of rows): no split / transpose copies.  Persistent CTAs (1 per SM), 10 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9
 // soft-max + epilogue warpgroups for query tile 0 / 1 (rows 0-127 / 128-255).  Shared memory holds ONE problem's operands
 // (hi + lo: up to 176 KB) with a full/empty mbarrier pair per operand group -- Q tile 0, Q tile 1, K, V -- so each group of the
 // next problem is re-loaded as soon as the last MMA reading it has retired (Q/K right after the scores, V after P V), i.e.
@@ -37,6 +37,8 @@ struct AttnTcParams
     int kv_bytes; // NKP * 128 rounded up to 1024
     float scale;  // 1/sqrt(64)
     int hilo;     // 1: split-precision operands (lo tensors present); 0: hi only
+    int reverse;  // 1: problems are taken last image first -- the qkv GEMM wrote its output in ascending row order, so the tail of the
+                  // QKV buffers is what the 126 MB L2 still holds when this kernel starts (like layernorm_f16_kernel)
     long long *trace; // dev only (VITB200_ATTN_TRACE): clock64 stamps of CTA 0, [problem < 16][slot < 32]; NULL in production
 };
 
@@ -148,38 +150,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // issued late (when the previous problem's MMAs retire); prefetching a problem ahead moves the HBM latency and the
             // bandwidth burst off that critical window -- the loads then come out of L2.
             auto prefetch = [&](int prob) {
-                const int b = prob / p.H, h = prob - b * p.H, row0 = b * p.N;
+                const int rp = p.reverse ? p.n_problems - 1 - prob : prob;
+                const int b = rp / p.H, h = rp - b * p.H, row0 = b * p.N;
                 for (int hl = 0; hl < (hilo ? 2 : 1); ++hl)
                 {
                     const CUtensorMap *mkv = hl ? &tmKVl : &tmKV, *mq = hl ? &tmQl : &tmQ;
-                    ptx::tma_prefetch_2d(mkv, p.D + h * 64, row0);
-                    for (int t = 0; t < p.n_mtiles; ++t) ptx::tma_prefetch_2d(mq, h * 64, row0 + t * 128);
-                    ptx::tma_prefetch_2d(mkv, 2 * p.D + h * 64, row0);
+                    ptx::tma_prefetch_3d(mkv, 0, row0, p.H + h);
+                    for (int t = 0; t < p.n_mtiles; ++t) ptx::tma_prefetch_3d(mq, 0, row0 + t * 128, h);
+                    ptx::tma_prefetch_3d(mkv, 0, row0, 2 * p.H + h);
                 }
             };
             int i = 0;
             for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
             {
                 const uint32_t ph = (uint32_t)(i & 1);
-                const int b = prob / p.H, h = prob - b * p.H;
+                const int rp = p.reverse ? p.n_problems - 1 - prob : prob; // (image, head) pairs are walked LAST FIRST, see AttnTcParams::reverse
+                const int b = rp / p.H, h = rp - b * p.H;
                 const int row0 = b * p.N;
                 ptx::mbar_wait(k_empty, ph ^ 1);
                 ptx::mbar_arrive_expect_tx(k_full, kv_tx);
-                ptx::tma_load_2d(sK(0), &tmKV, k_full, p.D + h * 64, row0);
-                if (hilo) ptx::tma_load_2d(sK(1), &tmKVl, k_full, p.D + h * 64, row0);
+                ptx::tma_load_3d(sK(0), &tmKV, k_full, 0, row0, p.H + h);
+                if (hilo) ptx::tma_load_3d(sK(1), &tmKVl, k_full, 0, row0, p.H + h);
                 for (int t = 0; t < p.n_mtiles; ++t)
                 {
                     ptx::mbar_wait(q_empty(t), ph ^ 1);
                     ptx::mbar_arrive_expect_tx(q_full(t), q_tx);
-                    ptx::tma_load_2d(sQ(0, t), &tmQ, q_full(t), h * 64, row0 + t * 128);
-                    if (hilo) ptx::tma_load_2d(sQ(1, t), &tmQl, q_full(t), h * 64, row0 + t * 128);
+                    ptx::tma_load_3d(sQ(0, t), &tmQ, q_full(t), 0, row0 + t * 128, h);
+                    if (hilo) ptx::tma_load_3d(sQ(1, t), &tmQl, q_full(t), 0, row0 + t * 128, h);
                 }
                 // K/Q of this problem are on their way; now ask L2 for everything the NEXT problem will need
                 if (prob + (int)gridDim.x < p.n_problems) prefetch(prob + (int)gridDim.x);
                 ptx::mbar_wait(v_empty, ph ^ 1);
                 ptx::mbar_arrive_expect_tx(v_full, kv_tx);
-                ptx::tma_load_2d(sV(0), &tmKV, v_full, 2 * p.D + h * 64, row0);
-                if (hilo) ptx::tma_load_2d(sV(1), &tmKVl, v_full, 2 * p.D + h * 64, row0);
+                ptx::tma_load_3d(sV(0), &tmKV, v_full, 0, row0, 2 * p.H + h);
+                if (hilo) ptx::tma_load_3d(sV(1), &tmKVl, v_full, 0, row0, 2 * p.H + h);
             }
         }
         __syncwarp();
@@ -269,7 +273,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             int i = 0;
             for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++i)
             {
-                const int b = prob / p.H, h = prob - b * p.H;
+                const int rp = p.reverse ? p.n_problems - 1 - prob : prob; // (image, head) pairs are walked LAST FIRST, see AttnTcParams::reverse
+                const int b = rp / p.H, h = rp - b * p.H;
                 if (q == 0) ATT_TRACE(8 * t + 0);
                 ptx::mbar_wait(s_full(t), i & 1);
                 ptx::tcgen05_fence_after();

@@ -158,18 +158,18 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 const int row0 = b * p.N;
                 ptx::mbar_wait(k_empty, (ip & 1) ^ 1); // both issuers have committed their last scores of the previous head
                 ptx::mbar_arrive_expect_tx(k_full, (uint32_t)(nbox * 8192));
-                for (int x = 0; x < nbox; ++x) ptx::tma_load_2d(sK + x * 8192, &tmKV64, k_full, p.D + h * 64, row0 + x * 64);
+                for (int x = 0; x < nbox; ++x) ptx::tma_load_3d(sK + x * 8192, &tmKV64, k_full, 0, row0 + x * 64, p.H + h);
                 for (int ti = 0; ti < p.n_tiles; ++ti, ++iq)
                 {
                     const int qb = iq & 1;
                     ptx::mbar_wait(q_empty(qb), ((iq >> 1) & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(q_full(qb), 16384u);
-                    ptx::tma_load_2d(sQ0 + qb * 16384, &tmQ, q_full(qb), h * 64, row0 + ti * 128);
+                    ptx::tma_load_3d(sQ0 + qb * 16384, &tmQ, q_full(qb), 0, row0 + ti * 128, h);
                     if (ti == 0)
                     {
                         ptx::mbar_wait(v_empty, (ip & 1) ^ 1);
                         ptx::mbar_arrive_expect_tx(v_full, (uint32_t)(nbox * 8192));
-                        for (int x = 0; x < nbox; ++x) ptx::tma_load_2d(sV + x * 8192, &tmKV64, v_full, 2 * p.D + h * 64, row0 + x * 64);
+                        for (int x = 0; x < nbox; ++x) ptx::tma_load_3d(sV + x * 8192, &tmKV64, v_full, 0, row0 + x * 64, 2 * p.H + h);
                     }
                 }
             }

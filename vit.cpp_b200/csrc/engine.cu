@@ -104,6 +104,25 @@ int make_tmap_tokens3d(CUtensorMap *m, const void *ptr, uint64_t images, uint64_
     return 0;
 }
 
+// 3-D f16 view of a HEAD-MAJOR q / k / v buffer [planes][plane_rows][64] (planes = 3 x heads: q heads, then k heads, then v heads;
+// plane_rows = the arena's token rows): dims {64, rows, planes}, box = 64 columns x box_rows rows x 1 plane, SWIZZLE_128B.  `rows` may be
+// smaller than plane_rows (the qkv epilogue's store map of a batch: rows past the batch are clipped).
+int make_tmap_heads3d(CUtensorMap *m, const void *ptr, uint64_t planes, uint64_t rows, uint64_t plane_rows, uint32_t box_rows)
+{
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {64, rows, planes};
+    cuuint64_t strides[2] = {128, plane_rows * 128};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(heads3d) failed (%d) planes=%llu rows=%llu box_rows=%u", (int)r,
+                                       (unsigned long long)planes, (unsigned long long)rows, box_rows);
+    return 0;
+}
+
 int make_tmap(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows)
 {
     PFN_tmapEncodeTiled enc = tmap_encoder();
@@ -582,7 +601,7 @@ int launch_attention_t(vitb200_engine *e, int B, cudaStream_t s)
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set[dev & 63] = smem;
     }
-    kern<<<B * H, NW * 32, smem, s>>>(e->QKV16, e->A16, N, D, H, Npad, 1.0f / sqrtf((float)(D / H)));
+    kern<<<B * H, NW * 32, smem, s>>>(e->QKV16, (size_t)e->max_batch * N, e->A16, N, D, H, Npad, 1.0f / sqrtf((float)(D / H)));
     CUDA_TRY(cudaGetLastError());
     e->launches++;
     return 0;
@@ -598,6 +617,7 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
     p.kv_bytes = (p.NKP * 128 + 1023) / 1024 * 1024;
     p.scale = 1.0f / sqrtf((float)(p.D / p.H));
     p.hilo = e->attn_hilo ? 1 : 0;
+    p.reverse = !(getenv("VITB200_ATTN_REVERSE") && atoi(getenv("VITB200_ATTN_REVERSE")) == 0);
     const int smem = attention_tc_smem_bytes(p.kv_bytes);
     static int smem_set[64] = {};
     int dev = 0;
@@ -729,6 +749,20 @@ int tap_f16(float *dst, const __half *src, size_t n, cudaStream_t s, const __hal
     return 0;
 }
 
+// debug tap of the q | k | v activations in the reference's [tokens][3 D] order (the device buffers are head-major: [3 H][rows][64])
+int tap_qkv(vitb200_engine *e, float *dst, int T, cudaStream_t s)
+{
+    if (!dst) return 0;
+    const int D = e->hp.hidden_size, H = e->hp.num_attention_heads;
+    const size_t plane_rows = (size_t)e->max_batch * e->N, n = (size_t)3 * H * plane_rows * 64;
+    std::vector<float> tmp(n);
+    if (tap_f16(tmp.data(), e->QKV16, n, s, e->attn_hilo ? e->QKV16L : nullptr)) return 1;
+    for (int t = 0; t < T; ++t)
+        for (int pl = 0; pl < 3 * H; ++pl)
+            memcpy(dst + (size_t)t * 3 * D + (size_t)pl * 64, tmp.data() + ((size_t)pl * plane_rows + t) * 64, 64 * sizeof(float));
+    return 0;
+}
+
 // The fixed kernel schedule == reference vit_encode_image (vit.cpp:718-941), batched over images.
 int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs, float *d_logits, int32_t *d_topk_idx,
                 float *d_topk_val, int k, cudaStream_t s, const vitb200_taps *taps)
@@ -747,8 +781,8 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         vitb200_engine::BatchMaps m;
         memset(&m, 0, sizeof(m));
         if (make_tmap_f32_box32(&m.X, e->X, (uint64_t)T, (uint64_t)D, (uint64_t)D) ||
-            make_tmap(&m.QKVh, e->QKV16, (uint64_t)T, 3 * (uint64_t)D, 3 * (uint64_t)D, 32) ||
-            (e->QKV16L && make_tmap(&m.QKVl, e->QKV16L, (uint64_t)T, 3 * (uint64_t)D, 3 * (uint64_t)D, 32)) ||
+            make_tmap_heads3d(&m.QKVh, e->QKV16, 3 * (uint64_t)e->hp.num_attention_heads, (uint64_t)T, (uint64_t)e->max_batch * N, 32) ||
+            (e->QKV16L && make_tmap_heads3d(&m.QKVl, e->QKV16L, 3 * (uint64_t)e->hp.num_attention_heads, (uint64_t)T, (uint64_t)e->max_batch * N, 32)) ||
             make_tmap(&m.H, e->H16, (uint64_t)T, 4 * (uint64_t)D, 4 * (uint64_t)D, 32))
             return 1;
         bm = e->batch_maps.emplace(B, m).first;
@@ -796,11 +830,11 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         }
         {
             GemmParams p{};
-            p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.out2 = e->QKV16L; p.ldo = 3 * D;
+            p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.out2 = e->QKV16L; p.ldo = 3 * D; p.headmajor = 1;
             ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
             if (launch_gemm(e, e->cta_group, L.qkv.bn, e->attn_hilo ? EPI_BIAS_F16_HILO : EPI_BIAS_F16, e->tmA_D, L.qkv.tm, tmQKVh, tmQKVl, p, s, e->num_sms)) return 1; // vit.cpp:820-821
         }
-        if (tap && tap_f16(taps->qkv, e->QKV16, (size_t)T * 3 * D, s, e->attn_hilo ? e->QKV16L : nullptr)) return 1;
+        if (tap && tap_qkv(e, taps->qkv, T, s)) return 1;
         {
             ProfScope ps(e, PK_ATTN, 4.0 * B * e->hp.num_attention_heads * (double)N * N * 64, s);
             if (launch_attention(e, B, s)) return 1; // vit.cpp:826-866
@@ -1092,16 +1126,16 @@ static int create_impl(const vitb200_hparams *hp, const vitb200_tensor *t, int n
         e->attn_tc_long = e->N > 224 && e->N <= ATT_LONG_MAX_KEYS && !force_mma;
         if (e->attn_tc_long)
         {
-            if (make_tmap(&e->tmQ, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
-                make_tmap(&e->tmKV64, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 64) ||
+            if (make_tmap_heads3d(&e->tmQ, e->QKV16, 3 * (uint64_t)hp->num_attention_heads, T, T, 128) ||
+                make_tmap_heads3d(&e->tmKV64, e->QKV16, 3 * (uint64_t)hp->num_attention_heads, T, T, 64) ||
                 make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)e->N, (uint64_t)D))
                 return bail(1);
         }
         if (e->attn_tc)
         {
             const int NKP = (e->N + 15) / 16 * 16;
-            if (make_tmap(&e->tmQ, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
-                make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP) ||
+            if (make_tmap_heads3d(&e->tmQ, e->QKV16, 3 * (uint64_t)hp->num_attention_heads, T, T, 128) ||
+                make_tmap_heads3d(&e->tmKV, e->QKV16, 3 * (uint64_t)hp->num_attention_heads, T, T, (uint32_t)NKP) ||
                 make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)e->N, (uint64_t)D))
                 return bail(1);
             // split-precision q, k, v (reference: f32 operands, vit.cpp:848,858); VITB200_ATTN_HILO=0 keeps the f16-only operands
@@ -1109,8 +1143,8 @@ static int create_impl(const vitb200_hparams *hp, const vitb200_tensor *t, int n
             if (e->attn_hilo)
             {
                 if (dev_alloc(e, &e->QKV16L, T * 3 * D) ||
-                    make_tmap(&e->tmQl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
-                    make_tmap(&e->tmKVl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP))
+                    make_tmap_heads3d(&e->tmQl, e->QKV16L, 3 * (uint64_t)hp->num_attention_heads, T, T, 128) ||
+                    make_tmap_heads3d(&e->tmKVl, e->QKV16L, 3 * (uint64_t)hp->num_attention_heads, T, T, (uint32_t)NKP))
                     return bail(1);
             }
         }
@@ -1220,12 +1254,21 @@ static int test_attention_impl(int device, int kernel, int B, int N, int H, cons
     const uint64_t T = (uint64_t)B * N;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("stream creation failed"));
     if (dev_alloc(e, &e->QKV16, (size_t)T * 3 * D) || dev_alloc(e, &e->A16, (size_t)T * D)) return bail(1);
-    if (cudaMemcpy(e->QKV16, qkv, (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
+    // the kernels read the HEAD-MAJOR layout the qkv GEMM writes ([3 H][T][64]); the caller hands over the reference's [T][3 D]
+    std::vector<uint16_t> hm((size_t)T * 3 * D);
+    auto to_head_major = [&](const uint16_t *src) {
+        for (uint64_t t = 0; t < T; ++t)
+            for (int pl = 0; pl < 3 * H; ++pl)
+                memcpy(&hm[((size_t)pl * T + t) * 64], src + (size_t)t * 3 * D + (size_t)pl * 64, 128);
+    };
+    to_head_major(qkv);
+    if (cudaMemcpy(e->QKV16, hm.data(), (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
     if (qkv_lo)
     {
         if (N > 224) return bail(fail("split-precision attention needs N <= 224"));
         if (dev_alloc(e, &e->QKV16L, (size_t)T * 3 * D)) return bail(1);
-        if (cudaMemcpy(e->QKV16L, qkv_lo, (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
+        to_head_major(qkv_lo);
+        if (cudaMemcpy(e->QKV16L, hm.data(), (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
         e->attn_hilo = true;
     }
     if (kernel == 0) kernel = N <= 224 ? 2 : (N <= ATT_LONG_MAX_KEYS ? 3 : 1);
@@ -1236,13 +1279,13 @@ static int test_attention_impl(int device, int kernel, int B, int N, int H, cons
     if (kernel >= 2)
     {
         const int NKP = (N + 15) / 16 * 16;
-        if (make_tmap(&e->tmQ, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
-            make_tmap(&e->tmKV, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)(NKP <= 224 ? NKP : 64)) ||
-            make_tmap(&e->tmKV64, e->QKV16, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 64) ||
+        if (make_tmap_heads3d(&e->tmQ, e->QKV16, 3 * (uint64_t)H, T, T, 128) ||
+            make_tmap_heads3d(&e->tmKV, e->QKV16, 3 * (uint64_t)H, T, T, (uint32_t)(NKP <= 224 ? NKP : 64)) ||
+            make_tmap_heads3d(&e->tmKV64, e->QKV16, 3 * (uint64_t)H, T, T, 64) ||
             make_tmap_tokens3d(&e->tmAO, e->A16, (uint64_t)B, (uint64_t)N, (uint64_t)D))
             return bail(1);
-        if (qkv_lo && (make_tmap(&e->tmQl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, 128) ||
-                       make_tmap(&e->tmKVl, e->QKV16L, T, 3 * (uint64_t)D, 3 * (uint64_t)D, (uint32_t)NKP)))
+        if (qkv_lo && (make_tmap_heads3d(&e->tmQl, e->QKV16L, 3 * (uint64_t)H, T, T, 128) ||
+                       make_tmap_heads3d(&e->tmKVl, e->QKV16L, 3 * (uint64_t)H, T, T, (uint32_t)NKP)))
             return bail(1);
     }
     if (launch_attention(e, B, e->stream)) return bail(1);

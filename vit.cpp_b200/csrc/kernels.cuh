@@ -212,23 +212,25 @@ __device__ __forceinline__ void att_scores(float (&s)[ATT_KC / 8][4], const uint
 
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
-attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int N, int D, int H, int Npad, float scale)
+attention_kernel(const __half *__restrict__ qkv, size_t plane_rows, __half *__restrict__ out, int N, int D, int H, int Npad, float scale)
+// qkv: the head-major buffer the qkv GEMM writes, [3 H planes][plane_rows][64]: q of head h in plane h, k in H + h, v in 2 H + h
 {
     extern __shared__ __align__(16) uint8_t att_smem[];
     const int b = blockIdx.x / H, h = blockIdx.x - b * H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint4 *sK4 = reinterpret_cast<uint4 *>(att_smem);
     uint4 *sV4 = sK4 + Npad * 8;
-    const size_t row_stride = (size_t)3 * D;
-    const __half *base = qkv + (size_t)b * N * row_stride + (size_t)h * 64;
+    const size_t row_stride = 64;
+    const __half *base = qkv + ((size_t)h * plane_rows + (size_t)b * N) * 64;       // q rows of this (image, head)
+    const size_t k_off = (size_t)H * plane_rows * 64, v_off = 2 * k_off;           // same rows in the k / v planes
     for (int idx = tid; idx < Npad * 8; idx += NWARPS * 32)
     {
         const int t = idx >> 3, c = idx & 7;
         uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
         if (t < N)
         {
-            kv = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)t * row_stride + D) + c);
-            vv = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)t * row_stride + 2 * D) + c);
+            kv = __ldg(reinterpret_cast<const uint4 *>(base + k_off + (size_t)t * row_stride) + c);
+            vv = __ldg(reinterpret_cast<const uint4 *>(base + v_off + (size_t)t * row_stride) + c);
         }
         sK4[t * 8 + (c ^ (t & 7))] = kv;
         sV4[t * 8 + (c ^ (t & 7))] = vv;

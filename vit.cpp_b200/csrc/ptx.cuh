@@ -153,6 +153,20 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *m, int c0, in
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// 3-D tiled load global -> shared (the head-major q / k / v planes: coordinates = column, token row, plane)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *m, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // CTA-pair variant: executed by both CTAs of a pair; the data lands in the executing CTA's shared memory, the
 // complete_tx goes to the mbarrier of the pair's leader (even) CTA (peer bit 24 of the shared::cluster address cleared)
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1)
