@@ -573,8 +573,42 @@ int launch_patchify(vitb200_engine *e, const float *img, __half *A, int B, cudaS
 int launch_layernorm(vitb200_engine *e, const float *x, size_t x_row_stride, const float *w, const float *b, __half *y, int rows, cudaStream_t s,
                      int rows_per_group = 0, size_t group_stride = 0)
 {
-    if (rows_per_group <= 0) rows_per_group = rows > 0 ? rows : 1; // one group: plain consecutive rows
     const int D = e->hp.hidden_size;
+    // block LayerNorms (all rows consecutive): the persistent bulk-copy kernel; VITB200_LN_TMA=0 keeps the row-per-warp kernel
+    static const bool ln_tma = !(getenv("VITB200_LN_TMA") && atoi(getenv("VITB200_LN_TMA")) == 0);
+    if (ln_tma && rows_per_group <= 0 && x_row_stride == (size_t)D && D % 128 == 0 && D <= 1024 && rows >= 8)
+    {
+        const int smem = layernorm_tma_smem_bytes(D);
+        const int nblk = (rows + LN_TMA_ROWS - 1) / LN_TMA_ROWS;
+        const int grid = std::min(nblk, 2 * e->num_sms);
+        auto launch = [&](auto kern) -> int {
+            // per kernel instantiation (all of them share this lambda's type: index by D / 128) and per device (one engine per device,
+            // possibly several per process)
+            static bool attr_set[9][64] = {};
+            int dev = 0;
+            CUDA_TRY(cudaGetDevice(&dev));
+            if (!attr_set[D / 128][dev & 63]) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set[D / 128][dev & 63] = true; }
+            CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(LN_TMA_THREADS), (size_t)smem, s, x, w, b, y, rows, e->hp.eps));
+            return 0;
+        };
+        int rc = 1;
+        switch (D / 128)
+        {
+        case 1: rc = launch(layernorm_tma_kernel<1>); break;
+        case 2: rc = launch(layernorm_tma_kernel<2>); break;
+        case 3: rc = launch(layernorm_tma_kernel<3>); break;
+        case 4: rc = launch(layernorm_tma_kernel<4>); break;
+        case 5: rc = launch(layernorm_tma_kernel<5>); break;
+        case 6: rc = launch(layernorm_tma_kernel<6>); break;
+        case 7: rc = launch(layernorm_tma_kernel<7>); break;
+        case 8: rc = launch(layernorm_tma_kernel<8>); break;
+        }
+        if (rc) return 1;
+        CUDA_TRY(cudaGetLastError());
+        e->launches++;
+        return 0;
+    }
+    if (rows_per_group <= 0) rows_per_group = rows > 0 ? rows : 1; // one group: plain consecutive rows
     const int threads = 256, rows_per_block = threads / 32;
     const int blocks = (rows + rows_per_block - 1) / rows_per_block;
     if (D <= 4 * 128) CUDA_TRY(launch_pdl(layernorm_f16_kernel<4>, dim3(blocks), dim3(threads), 0, s, x, x_row_stride, rows_per_group, group_stride, w, b, y, rows, D, e->hp.eps));
@@ -1271,6 +1305,9 @@ static int test_attention_impl(int device, int kernel, int B, int N, int H, cons
         if (cudaMemcpy(e->QKV16L, hm.data(), (size_t)T * 3 * D * 2, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail("H2D failed"));
         e->attn_hilo = true;
     }
+    // cudaMemcpy from pageable memory may return before the DMA has landed, and the kernels below run on a NON-BLOCKING stream (no implicit
+    // ordering with the legacy stream the copies used): wait for the device before launching
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail("device sync after upload failed"));
     if (kernel == 0) kernel = N <= 224 ? 2 : (N <= ATT_LONG_MAX_KEYS ? 3 : 1);
     if (kernel == 2 && N > 224) return bail(fail("tcgen05 single-block attention needs N <= 224"));
     if (kernel == 3 && (N <= 128 || N > ATT_LONG_MAX_KEYS)) return bail(fail("tcgen05 two-sweep attention needs 128 < N <= %d", ATT_LONG_MAX_KEYS));
