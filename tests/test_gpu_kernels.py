@@ -184,3 +184,21 @@ def test_q8_0_gemm_matches_the_reference_integer_dot(M, N, K):
     scale = np.abs(y_ref).max(axis=1, keepdims=True)
     err = (np.abs(y - y_ref) / scale).max()
     assert err <= 1e-5, f"q8_0 GEMM error {err:.3e}"
+
+
+# ---- LayerNorm: the persistent bulk-copy kernel (D % 128 == 0, >= 8 rows) and the row-per-warp kernel behind the same launcher -----------
+@pytest.mark.parametrize("rows,D", [(1, 768), (7, 768), (8, 768), (9, 768), (591, 768), (1154, 1024), (4097, 128), (34, 128), (50, 192), (2, 384)])
+def test_layernorm_matches_the_restatement(rows, D):
+    """Row counts around the 8-row block size (partial last block, fewer rows than one block -> row-per-warp kernel), more blocks than
+    resident CTAs, hidden sizes of every model in the tests; against the oracle's ggml_norm * w + b rounded to f16 (the GEMM's src1
+    conversion): at most one f16 ulp apart (the reference sums in double, the kernel in f32)."""
+    rng = np.random.default_rng(rows * 131 + D)
+    x = (rng.standard_normal((rows, D)) * rng.uniform(0.5, 4.0, (rows, 1)) + rng.uniform(-1, 1, (rows, 1))).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, D).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, D).astype(np.float32)
+    y = eng.test_layernorm(x, w, b)
+    ref = rs.round_f16(rs.layernorm(x, w, b))
+    ulp = np.spacing(np.abs(ref).astype(np.float16)).astype(np.float32)
+    assert np.isfinite(y).all()
+    assert (np.abs(y - ref) <= ulp + 1e-12).all(), float((np.abs(y - ref) / ulp).max())
+    assert (y == ref).mean() > 0.995

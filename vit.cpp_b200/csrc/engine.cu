@@ -1669,6 +1669,44 @@ int vitb200_test_gemm(int device, int M, int N, int K, int epilogue, const uint1
     return rc;
 }
 
+// Stand-alone run of the block LayerNorm as the engine launches it (persistent bulk-copy kernel for hidden sizes that are a multiple of 128
+// and >= 8 rows, the row-per-warp kernel otherwise): x [rows][D] f32 -> y [rows][D] (f16 results widened to f32).
+int vitb200_test_layernorm(int device, int rows, int D, const float *x, const float *w, const float *b, float eps, float *y)
+{
+    if (!x || !w || !b || !y || rows < 1 || D < 4 || D % 4 != 0 || D > 2048) return fail("bad argument");
+    VB_NOEXCEPT_BEGIN
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: the vit.cpp_b200 forward path has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    vitb200_engine e{};
+    e.hp.hidden_size = D; e.hp.eps = eps; e.num_sms = prop.multiProcessorCount; e.device = device;
+    float *dx = nullptr, *dw = nullptr, *db = nullptr;
+    __half *dy = nullptr;
+    int rc = 1;
+    do
+    {
+        if (cudaMalloc(&dx, (size_t)rows * D * 4) || cudaMalloc(&dw, (size_t)D * 4) || cudaMalloc(&db, (size_t)D * 4) || cudaMalloc(&dy, (size_t)rows * D * 2)) { fail("cudaMalloc failed"); break; }
+        cudaMemcpy(dx, x, (size_t)rows * D * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dw, w, (size_t)D * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(db, b, (size_t)D * 4, cudaMemcpyHostToDevice);
+        cudaMemset(dy, 0xFF, (size_t)rows * D * 2);
+        if (cudaDeviceSynchronize() != cudaSuccess) { fail("device sync failed"); break; }
+        if (launch_layernorm(&e, dx, (size_t)D, dw, db, dy, rows, 0)) break;
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { fail("LayerNorm kernel failed: %s", cudaGetErrorString(err)); break; }
+        std::vector<__half> tmp((size_t)rows * D);
+        cudaMemcpy(tmp.data(), dy, tmp.size() * 2, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < tmp.size(); ++i) y[i] = __half2float(tmp[i]);
+        rc = 0;
+    } while (0);
+    cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dy);
+    return rc;
+    VB_NOEXCEPT_END((void)0)
+}
+
 // q8_0 linear layer on the integer tensor cores (gemm_q8_tcgen05.cuh; prototype for BASELINE.json configs[4]): x [M][K] f32 is
 // quantised on the device exactly as the reference quantises activation rows, w is a q8_0 tensor in the model-file layout
 // ([N][K/32] blocks of {f16 d; int8 q[32]}, ggml-quants.h:42-46).  Outputs: y [M][N] f32, and (optional) the quantised activations

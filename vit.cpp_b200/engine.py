@@ -84,6 +84,7 @@ def lib():
         L.vitb200_test_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         L.vitb200_test_dequant.argtypes = [i32, vp, C.c_int64, vp]
         L.vitb200_test_gemm_q8.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
+        L.vitb200_test_layernorm.argtypes = [i32, i32, i32, vp, vp, vp, C.c_float, vp]
         L.vitb200_test_attention.argtypes = [i32, i32, i32, i32, i32, vp, vp]
         L.vitb200_test_attention_hilo.argtypes = [i32, i32, i32, i32, vp, vp, vp]
         _lib = L
@@ -349,3 +350,14 @@ def test_gemm_q8(x, w_blocks, bias, device: int = 0, iters: int = 0):
     _check(lib().vitb200_test_gemm_q8(device, M, N, K, x.ctypes.data, w.ctypes.data, b.ctypes.data, y.ctypes.data, xq.ctypes.data,
                                       xd.ctypes.data, iters, C.cast(C.pointer(ms), C.c_void_p)), "vitb200_test_gemm_q8")
     return y, xq, xd, (ms.value if iters > 0 else None)
+
+
+def test_layernorm(x, w, b, eps: float = 1e-6, device: int = 0):
+    """The block LayerNorm kernel alone (vitb200_test_layernorm): x float32 [rows][D] -> float32 [rows][D] (f16 values widened)."""
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    y = np.empty_like(x)
+    _check(lib().vitb200_test_layernorm(device, x.shape[0], x.shape[1], x.ctypes.data, w.ctypes.data, b.ctypes.data, eps, y.ctypes.data),
+           "vitb200_test_layernorm")
+    return y
