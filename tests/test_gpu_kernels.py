@@ -191,7 +191,7 @@ def test_q8_0_gemm_matches_the_reference_integer_dot(M, N, K):
 def test_layernorm_matches_the_restatement(rows, D):
     """Row counts around the 8-row block size (partial last block, fewer rows than one block -> row-per-warp kernel), more blocks than
     resident CTAs, hidden sizes of every model in the tests; against the oracle's ggml_norm * w + b rounded to f16 (the GEMM's src1
-    conversion): at most one f16 ulp apart (the reference sums in double, the kernel in f32)."""
+    conversion): at most one f16 ulp apart (the reference sums in double, the kernel in f32), bit-equal on > 99.5 % of the elements."""
     rng = np.random.default_rng(rows * 131 + D)
     x = (rng.standard_normal((rows, D)) * rng.uniform(0.5, 4.0, (rows, 1)) + rng.uniform(-1, 1, (rows, 1))).astype(np.float32)
     w = rng.uniform(0.5, 1.5, D).astype(np.float32)
@@ -200,5 +200,7 @@ def test_layernorm_matches_the_restatement(rows, D):
     ref = rs.round_f16(rs.layernorm(x, w, b))
     ulp = np.spacing(np.abs(ref).astype(np.float16)).astype(np.float32)
     assert np.isfinite(y).all()
-    assert (np.abs(y - ref) <= ulp + 1e-12).all(), float((np.abs(y - ref) / ulp).max())
+    # one f16 ulp, or -- where (x - mean) * scale * w and b cancel to a result near zero, whose ulp is tiny -- the f32 rounding of the
+    # un-cancelled terms (|terms| < 10 here)
+    assert (np.abs(y - ref) <= np.maximum(ulp, 4e-6)).all(), float((np.abs(y - ref) / np.maximum(ulp, 4e-6)).max())
     assert (y == ref).mean() > 0.995
