@@ -454,6 +454,16 @@ struct ProfScope
     }
 };
 
+// L2 eviction hints on the big streamed-once transfers (profiles/microbench_r02.md: fc1 -4 %, LayerNorm -2 %, proj / fc2 -1 % at batch 256 --
+// the 465 MB of q, k, v and the 310 MB MLP hidden buffer no longer push the LayerNorm output, which the next GEMM reads nine to twelve
+// times, out of the 126 MB L2).  VITB200_L2HINT = bit mask, default 7: 1 = qkv / fc1 output stores evict_first, 2 = attention operand
+// loads evict_first, 4 = LayerNorm input loads evict_first (8 = LayerNorm output stores evict_last: measured worse, off).
+int l2_hint_mask()
+{
+    static const int m = getenv("VITB200_L2HINT") ? atoi(getenv("VITB200_L2HINT")) : 7;
+    return m;
+}
+
 // Programmatic dependent launch for the per-layer kernels (GEMMs, attention, LayerNorm): each of them ends its prologue with
 // griddepcontrol.launch_dependents + griddepcontrol.wait (ptx.cuh), so kernel k+1's barrier init / TMEM allocation / descriptor
 // prefetch runs on the SMs kernel k has already left.  VITB200_PDL=0 launches them fully serialised.
@@ -588,7 +598,8 @@ int launch_layernorm(vitb200_engine *e, const float *x, size_t x_row_stride, con
             int dev = 0;
             CUDA_TRY(cudaGetDevice(&dev));
             if (!attr_set[D / 128][dev & 63]) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set[D / 128][dev & 63] = true; }
-            CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(LN_TMA_THREADS), (size_t)smem, s, x, w, b, y, rows, e->hp.eps));
+            CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(LN_TMA_THREADS), (size_t)smem, s, x, w, b, y, rows, e->hp.eps,
+                                (unsigned long long)((l2_hint_mask() & 4) ? ptx::L2_EVICT_FIRST : 0), (unsigned long long)((l2_hint_mask() & 8) ? ptx::L2_EVICT_LAST : 0)));
             return 0;
         };
         int rc = 1;
@@ -651,6 +662,7 @@ int launch_attention_tc(vitb200_engine *e, int B, cudaStream_t s)
     p.kv_bytes = (p.NKP * 128 + 1023) / 1024 * 1024;
     p.scale = 1.0f / sqrtf((float)(p.D / p.H));
     p.hilo = e->attn_hilo ? 1 : 0;
+    p.load_policy = (l2_hint_mask() & 2) ? ptx::L2_EVICT_FIRST : 0;
     p.reverse = !(getenv("VITB200_ATTN_REVERSE") && atoi(getenv("VITB200_ATTN_REVERSE")) == 0);
     const int smem = attention_tc_smem_bytes(p.kv_bytes);
     static int smem_set[64] = {};
@@ -864,7 +876,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         }
         {
             GemmParams p{};
-            p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.out2 = e->QKV16L; p.ldo = 3 * D; p.headmajor = 1;
+            p.M = T; p.N = 3 * D; p.K = D; p.bias = L.qkv.b; p.out = e->QKV16; p.out2 = e->QKV16L; p.ldo = 3 * D; p.headmajor = 1; p.store_policy = (l2_hint_mask() & 1) ? ptx::L2_EVICT_FIRST : 0;
             ProfScope ps(e, PK_QKV, 2.0 * p.M * p.N * p.K, s);
             if (launch_gemm(e, e->cta_group, L.qkv.bn, e->attn_hilo ? EPI_BIAS_F16_HILO : EPI_BIAS_F16, e->tmA_D, L.qkv.tm, tmQKVh, tmQKVl, p, s, e->num_sms)) return 1; // vit.cpp:820-821
         }
@@ -892,7 +904,7 @@ int run_forward(vitb200_engine *e, const float *d_images, int B, float *d_probs,
         if (tap && tap_f16(taps->ln2, e->A16, (size_t)T * D, s)) return 1;
         {
             GemmParams p{};
-            p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D;
+            p.M = T; p.N = 4 * D; p.K = D; p.bias = L.fc1.b; p.out = e->H16; p.ldo = 4 * D; p.store_policy = (l2_hint_mask() & 1) ? ptx::L2_EVICT_FIRST : 0;
             ProfScope ps(e, PK_FC1, 2.0 * p.M * p.N * p.K, s);
             if (launch_gemm(e, e->cta_group, L.fc1.bn, EPI_BIAS_GELU_F16, e->tmA_D, L.fc1.tm, tmH, tmH, p, s, e->num_sms)) return 1; // vit.cpp:889-893
         }

@@ -43,6 +43,8 @@ struct GemmParams
     void *out;          // f16 or f32, row-major, leading dimension ldo
     void *out2;         // EPI_BIAS_F16_HILO: the lo halves, same shape as out
     int ldo;
+    unsigned long long store_policy; // f16 epilogues: L2 eviction hint of the output's TMA stores (0 = none; ptx::L2_EVICT_FIRST for outputs that are
+                        // read once by the next kernel and are larger than the L2 anyway)
     int headmajor;      // f16 epilogues: 1 = the output is HEAD-MAJOR, [N / 64 planes][M rows][64] (tmX / tmO2 are 3-D maps: column, row, plane):
                         // every 64-column pass is one head's slice, stored as ONE contiguous 4-KB box instead of 32 row pieces of 128 B that lie
                         // ldo * 2 bytes apart -- what the attention kernels then read back as contiguous tiles (qkv)
@@ -782,7 +784,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
                     if (lane == 0)
                     {
-                        if (p.headmajor) ptx::tma_store_3d(part == 0 ? &tmX : &tmO2, stg_u32, 0, m0, (n0 + c) >> 6);
+                        if (p.store_policy)
+                        {
+                            if (p.headmajor) ptx::tma_store_3d_hint(part == 0 ? &tmX : &tmO2, stg_u32, 0, m0, (n0 + c) >> 6, p.store_policy);
+                            else ptx::tma_store_2d_hint(part == 0 ? &tmX : &tmO2, stg_u32, n0 + c, m0, p.store_policy);
+                        }
+                        else if (p.headmajor) ptx::tma_store_3d(part == 0 ? &tmX : &tmO2, stg_u32, 0, m0, (n0 + c) >> 6);
                         else ptx::tma_store_2d(part == 0 ? &tmX : &tmO2, stg_u32, n0 + c, m0);
                         ptx::tma_store_commit();
                     }

@@ -186,7 +186,8 @@ __host__ __device__ inline int layernorm_tma_smem_bytes(int D) { return 128 + LN
 
 template <int NV> // float4 per lane = D / 128
 __global__ void __launch_bounds__(LN_TMA_THREADS, 2)
-layernorm_tma_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, __half *__restrict__ y, int rows, float eps)
+layernorm_tma_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, __half *__restrict__ y, int rows, float eps,
+                     unsigned long long load_policy, unsigned long long store_policy) // L2 eviction hints of the bulk copies (0 = none)
 {
     constexpr int D = NV * 128;
     extern __shared__ uint8_t ln_smem_raw[];
@@ -219,7 +220,8 @@ layernorm_tma_kernel(const float *__restrict__ x, const float *__restrict__ w, c
                 const int nr = rows - row0 < LN_TMA_ROWS ? rows - row0 : LN_TMA_ROWS;
                 ptx::mbar_wait(empty_bar(st), ph ^ 1);
                 ptx::mbar_arrive_expect_tx(full_bar(st), (uint32_t)(nr * D * 4));
-                ptx::bulk_load_1d(s_in + st * IN_BYTES, x + (size_t)row0 * D, (uint32_t)(nr * D * 4), full_bar(st));
+                if (load_policy) ptx::bulk_load_1d_hint(s_in + st * IN_BYTES, x + (size_t)row0 * D, (uint32_t)(nr * D * 4), full_bar(st), load_policy);
+                else ptx::bulk_load_1d(s_in + st * IN_BYTES, x + (size_t)row0 * D, (uint32_t)(nr * D * 4), full_bar(st));
                 if (++st == LN_TMA_STAGES) { st = 0; ph ^= 1; }
             }
         }
@@ -285,7 +287,8 @@ layernorm_tma_kernel(const float *__restrict__ x, const float *__restrict__ w, c
             ptx::named_bar_sync(1, 32 * LN_TMA_ROWS);
             if (threadIdx.x == 0)
             {
-                ptx::bulk_store_1d(y + (size_t)row0 * D, ob, (uint32_t)(nr * D * 2));
+                if (store_policy) ptx::bulk_store_1d_hint(y + (size_t)row0 * D, ob, (uint32_t)(nr * D * 2), store_policy);
+                else ptx::bulk_store_1d(y + (size_t)row0 * D, ob, (uint32_t)(nr * D * 2));
                 ptx::tma_store_commit();
             }
             if (++st == LN_TMA_STAGES) { st = 0; ph ^= 1; }

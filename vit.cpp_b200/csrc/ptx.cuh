@@ -228,6 +228,42 @@ __device__ __forceinline__ void tma_store_wait_group()
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---------------------------------------------------------------- L2 eviction-priority hints on bulk / tensor copies
+// 64-bit cache policies as produced by createpolicy.fractional.L2::evict_*.b64 with fraction 1.0 (the encodings CUTLASS ships as
+// TMA::CacheHintSm90): streamed-once data (evict_first) should not push reused operands out of the 126 MB L2.
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *m, uint32_t smem_src, int c0, int c1, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap *m, uint32_t smem_src, int c0, int c1, int c2, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_hint(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d_hint(void *gdst, uint32_t smem_src, uint32_t bytes, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_src), "r"(bytes), "l"(pol)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tcgen05_alloc(uint32_t smem_dst, uint32_t ncols)
 {
