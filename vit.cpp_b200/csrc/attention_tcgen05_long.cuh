@@ -40,6 +40,7 @@ struct AttnLongParams
     int nb;          // sweep B's key blocks (2..ATT_LONG_MAX_BLOCKS) of <= 96 keys
     int key0[9];     // first key of block j (att_long_block_key0), key0[nb] = NKP: read from the constant bank, no divisions on the device
     float scale;     // 1/sqrt(64)
+    unsigned long long load_policy; // L2 eviction hint of the operand loads (0 = none): q, k, v are read exactly once
     long long *trace; // dev only (VITB200_ATTN_TRACE): clock64 stamps of CTA 0, [tile < 16][slot < 32] (warpgroup w writes slots 8 w ..); NULL in production
 };
 
@@ -150,6 +151,10 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         // ===================== TMA producer: K, V of the head once; Q tile number s of the CTA goes to slot s & 1 =====================
         if (lane == 0)
         {
+            auto ld3 = [&](uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2) {
+                if (p.load_policy) ptx::tma_load_3d_hint(dst, m, bar, c0, c1, c2, p.load_policy);
+                else ptx::tma_load_3d(dst, m, bar, c0, c1, c2);
+            };
             int ip = 0, iq = 0;
             const int nbox = p.kv_rows / 64;
             for (int prob = blockIdx.x; prob < p.n_problems; prob += gridDim.x, ++ip)
@@ -158,18 +163,18 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 const int row0 = b * p.N;
                 ptx::mbar_wait(k_empty, (ip & 1) ^ 1); // both issuers have committed their last scores of the previous head
                 ptx::mbar_arrive_expect_tx(k_full, (uint32_t)(nbox * 8192));
-                for (int x = 0; x < nbox; ++x) ptx::tma_load_3d(sK + x * 8192, &tmKV64, k_full, 0, row0 + x * 64, p.H + h);
+                for (int x = 0; x < nbox; ++x) ld3(sK + x * 8192, &tmKV64, k_full, 0, row0 + x * 64, p.H + h);
                 for (int ti = 0; ti < p.n_tiles; ++ti, ++iq)
                 {
                     const int qb = iq & 1;
                     ptx::mbar_wait(q_empty(qb), ((iq >> 1) & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(q_full(qb), 16384u);
-                    ptx::tma_load_3d(sQ0 + qb * 16384, &tmQ, q_full(qb), 0, row0 + ti * 128, h);
+                    ld3(sQ0 + qb * 16384, &tmQ, q_full(qb), 0, row0 + ti * 128, h);
                     if (ti == 0)
                     {
                         ptx::mbar_wait(v_empty, (ip & 1) ^ 1);
                         ptx::mbar_arrive_expect_tx(v_full, (uint32_t)(nbox * 8192));
-                        for (int x = 0; x < nbox; ++x) ptx::tma_load_3d(sV + x * 8192, &tmKV64, v_full, 0, row0 + x * 64, 2 * p.H + h);
+                        for (int x = 0; x < nbox; ++x) ld3(sV + x * 8192, &tmKV64, v_full, 0, row0 + x * 64, 2 * p.H + h);
                     }
                 }
             }

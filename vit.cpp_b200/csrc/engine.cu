@@ -586,7 +586,8 @@ int launch_layernorm(vitb200_engine *e, const float *x, size_t x_row_stride, con
     const int D = e->hp.hidden_size;
     // block LayerNorms (all rows consecutive): the persistent bulk-copy kernel; VITB200_LN_TMA=0 keeps the row-per-warp kernel
     static const bool ln_tma = !(getenv("VITB200_LN_TMA") && atoi(getenv("VITB200_LN_TMA")) == 0);
-    if (ln_tma && rows_per_group <= 0 && x_row_stride == (size_t)D && D % 128 == 0 && D <= 1024 && rows >= 8)
+    // (two CTAs per SM must fit: with one, as for D = 1024, it is slower than the row-per-warp kernel -- 4.98 against 3.9 ms per ViT-L forward)
+    if (ln_tma && rows_per_group <= 0 && x_row_stride == (size_t)D && D % 128 == 0 && 2 * (layernorm_tma_smem_bytes(D) + 1024) <= 233472 && rows >= 8)
     {
         const int smem = layernorm_tma_smem_bytes(D);
         const int nblk = (rows + LN_TMA_ROWS - 1) / LN_TMA_ROWS;
@@ -719,6 +720,7 @@ int launch_attention_tc_long(vitb200_engine *e, int B, cudaStream_t s)
         if (p.nb < 2) p.nb = 2;                  // the sweep-B pipeline alternates between two buffers
     }
     p.scale = 1.0f / sqrtf((float)(p.D / p.H));
+    p.load_policy = (l2_hint_mask() & 2) ? ptx::L2_EVICT_FIRST : 0;
     if (p.nb > ATT_LONG_MAX_BLOCKS || (p.NKP + 31) / 32 < p.nb)
         return fail("attention: %d tokens cannot be cut into 2..%d key blocks", e->N, ATT_LONG_MAX_BLOCKS);
     for (int j = 0; j < p.nb; ++j) p.key0[j] = att_long_block_key0(p.NKP, p.nb, j);
